@@ -1,0 +1,211 @@
+/* gravinv_b200.h -- C ABI of libgravinv_b200.so (sm_100a CUDA), the drop-in boundary for the
+ * GravInv3DHMC inversion hot path.
+ *
+ * The reference (ChuWeiEr/GravInv3DHMC) is pure Python and has no FFI registry; the seams this
+ * library replaces are its two native leaf calls and the numpy/scipy arithmetic of the sampler
+ * (reference paths are relative to the reference root):
+ *
+ *   gi_prism_gz_assemble     <- gravmag/_prism.pyx:263-290 gz()  called per prism by
+ *                               gravmag/prism.py:291-316 _gz (one kernel2d column per prism)
+ *   gi_tess_gz_assemble      <- gravmag/_tesseroid_numba.py:25-72 engine(kernelz) called per
+ *                               tesseroid by gravmag/tesseroid.py:189-232 _forward_model
+ *   gi_colsumsq, gi_weights_from_sumsq, gi_scale_columns
+ *                            <- inversion/potential.py:232-264 sensitivityWeighting
+ *   gi_gemv_fwd / gi_residual / gi_gemv_adj / gi_update
+ *                            <- inversion/potential.py:688-717 data_all, :719-810 model_*_all,
+ *                               :812-845 misfit_and_grad and the body of
+ *                               inversion/hmc.py:85-177 _leapfrog
+ *   gi_hmc_*                 <- inversion/hmc.py:85-177 _leapfrog, :252-343 sample (one proposal)
+ *   gi_dwt_db4_* / gi_csr_spmv
+ *                            <- gravmag/compressor1D.py:45-60, compressor3D.py:47-68 modelcompressor
+ *
+ * Conventions
+ *   - every function returns GI_OK (0) or a negative GI_ERR_* code and never throws;
+ *     gi_last_error() returns a thread-local message for the last failure.
+ *   - pointers named *_dev are CUDA device pointers owned by the caller (e.g. torch
+ *     Tensor.data_ptr()); pointers named *_host are host pointers (pinned memory makes the
+ *     copies asynchronous).  No torch types cross this boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - all arithmetic is IEEE binary64; matrices are row-major with leading dimension `ld`
+ *     (in doubles, a multiple of 4; columns [M, ld) must be zero).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     GI_ERR_CUDA.
+ */
+#ifndef GRAVINV_B200_H
+#define GRAVINV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GI_ABI_VERSION 1
+
+#define GI_OK 0
+#define GI_ERR_INVALID (-1)  /* bad argument (ValueError in the Python layer) */
+#define GI_ERR_CUDA (-2)     /* CUDA runtime error / no device */
+#define GI_ERR_OVERFLOW (-3) /* tesseroid subdivision stack overflow (OverflowError, _tesseroid_numba.py:53-54) */
+#define GI_ERR_NOMEM (-4)
+
+/* regularisers, inversion/potential.py:831-836 */
+#define GI_REG_DAMPING 0
+#define GI_REG_MS 1
+#define GI_REG_SMOOTHNESS 2
+#define GI_REG_TV 3
+/* boundary constraint, inversion/hmc.py:271-278 */
+#define GI_CONSTRAINT_MANDATORY 0
+#define GI_CONSTRAINT_LOGARITHMIC 1
+
+int gi_abi_version(void);
+const char *gi_last_error(void);
+/* sm count, compute capability, L2 bytes of the current device */
+int gi_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *l2_bytes);
+
+/* ---- sensitivity-matrix assembly -------------------------------------------------------- */
+/* G[l*ld + c] = scale * sum over the 8 corners of prism c at observation l (gz, closed form).
+ * bounds_dev is [M][6] = x1,x2,y1,y2,z1,z2 of the ACTIVE prisms in mesh order.
+ * Columns [M, ld) are written as zeros.  Rows [row0, row0+nrows) of the observation arrays
+ * are assembled into rows [0, nrows) of G (row sharding across GPUs). */
+int gi_prism_gz_assemble(const double *xp_dev, const double *yp_dev, const double *zp_dev,
+                         int64_t nrows, const double *bounds_dev, int64_t M, double scale,
+                         double *G_dev, int64_t ld, void *stream);
+
+/* Tesseroid gz, 2x2x2 Gauss-Legendre with the reference's LIFO adaptive subdivision.
+ * Inputs are the converted coordinates of gravmag/tesseroid.py:109-123.
+ * status_dev is int32[2]: [0] accumulates the reference's error_code (-1 per refused split),
+ * [1] is set to 1 if any pair overflowed the 100-entry stack (that entry is NaN).
+ * G = (raw * scale1) * scale2  as in gravmag/tesseroid.py:430. */
+int gi_tess_gz_assemble(const double *lon_dev, const double *sinlat_dev, const double *coslat_dev,
+                        const double *radius_dev, int64_t nrows, const double *bounds_dev,
+                        int64_t M, double ratio, double scale1, double scale2, double *G_dev,
+                        int64_t ld, int32_t *status_dev, void *stream);
+
+/* Forward field of a density model without storing G (prism.gz `result`, prism.py:291-316):
+ * res[l] = scale * sum_c dens[c] * gz(l, c), accumulated corner by corner in reference order. */
+int gi_prism_gz_forward(const double *xp_dev, const double *yp_dev, const double *zp_dev,
+                        int64_t nrows, const double *bounds_dev, const double *dens_dev, int64_t M,
+                        double scale, double *res_dev, void *stream);
+
+/* ---- sensitivity weighting (potential.py:232-264) ---------------------------------------- */
+/* out[c] (+)= sum_l G[l][c]^2, rows summed sequentially in row order. */
+int gi_colsumsq(const double *G_dev, int64_t nrows, int64_t M, int64_t ld, double *out_dev,
+                int accumulate, void *stream);
+/* wm = sumsq^weightfactor, wminv = 1/wm, wmsq = wm*wm */
+int gi_weights_from_sumsq(const double *sumsq_dev, int64_t M, double weightfactor, double *wm_dev,
+                          double *wminv_dev, double *wmsq_dev, void *stream);
+/* G[l][c] *= colscale[c] in place (Aw = A @ WmInv) */
+int gi_scale_columns(double *G_dev, int64_t nrows, int64_t M, int64_t ld,
+                     const double *colscale_dev, void *stream);
+
+/* ---- leapfrog building blocks (used directly by the row-sharded multi-GPU driver) -------- */
+typedef struct gi_plan gi_plan; /* tiling + workspace for one (nrows, M, ld, nchains) problem */
+
+int gi_plan_create(int64_t nrows, int64_t M, int64_t ld, int32_t nchains, gi_plan **out);
+int gi_plan_destroy(gi_plan *plan);
+/* number of kernels the plan launches for one fwd / adj pass (for launch accounting) */
+int gi_plan_info(const gi_plan *plan, int64_t *fwd_tiles, int64_t *adj_tiles,
+                 int64_t *workspace_bytes);
+
+/* d = G x  (x has ld entries, zero padded).  Deterministic two-stage reduction. */
+int gi_gemv_fwd(gi_plan *plan, const double *G_dev, const double *x_dev, double *d_dev,
+                void *stream);
+/* sums_dev[0] = sum_l (d[l] + fix[l])   (fix_dev may be NULL) */
+int gi_data_sum(gi_plan *plan, const double *d_dev, const double *fix_dev, double *sums_dev,
+                void *stream);
+/* r[l] = (d[l] + fix[l] - mean) - dobs_c[l];  sums_dev[1] = sum r^2.  mean = *mean_dev. */
+int gi_residual(gi_plan *plan, const double *d_dev, const double *fix_dev,
+                const double *dobs_c_dev, const double *mean_dev, double *r_dev, double *sums_dev,
+                void *stream);
+/* g = G^T r (no factor 2; the caller's update applies it).  Deterministic. */
+int gi_gemv_adj(gi_plan *plan, const double *G_dev, const double *r_dev, double *g_dev,
+                void *stream);
+
+typedef struct {
+    int32_t reg_kind;   /* GI_REG_* */
+    int32_t constraint; /* GI_CONSTRAINT_* */
+    int32_t nz, ny, nx; /* grid shape (Smoothness / TV need nz*ny*nx == M) */
+    int32_t reserved;
+    double alpha;      /* RegulFactor */
+    double beta;       /* MS / TV focusing parameter */
+    double log_factor; /* logarithmic constraint */
+} gi_reg_params;
+
+/* One fused M-vector pass (hmc.py:114-152 + potential.py:719-810):
+ *   grad = 2*gdata + alpha*dR/dmw(mw - mwapr);  Um = R(mw - mwapr)
+ *   p   -= pcoef * grad
+ *   if advance: x += dt*p; clamp to [low, high] and flip p (mandatory) ; mw_out = mw(x)
+ * gdata_dev holds G^T r (already summed over ranks).  sums_dev[2] = Um, sums_dev[3] = 0.5*p.p
+ * (after the update).  grad_out_dev may be NULL. x_in/x_out and mw_in/mw_out may not alias. */
+int gi_update(gi_plan *plan, const gi_reg_params *reg, const double *gdata_dev,
+              const double *x_in_dev, const double *mw_in_dev, const double *mwapr_dev,
+              const double *wmsq_dev, const double *low_dev, const double *high_dev, double *p_dev,
+              double *x_out_dev, double *mw_out_dev, double *grad_out_dev, double pcoef, double dt,
+              int advance, double *sums_dev, void *stream);
+
+/* ---- single-GPU device-resident sampler --------------------------------------------------- */
+typedef struct gi_hmc gi_hmc;
+
+typedef struct {
+    int64_t N, M, ld;
+    int32_t fixed; /* potential.py:699-703: add grav_fix to the forward data */
+    int32_t reserved;
+    gi_reg_params reg;
+} gi_hmc_config;
+
+typedef struct {
+    int32_t accept;
+    int32_t L;
+    double U, U_data, U_model; /* of the state the chain is in AFTER the proposal */
+    double Hcur, Hnew;
+    double Unew, Unew_data, Unew_model; /* of the proposed end point */
+} gi_hmc_result;
+
+/* G_dev (N x ld, weighted kernel Aw) stays owned by the caller and must outlive the handle.
+ * Host vectors (length M: low, high, mwapr, wmsq(optional); length N: dobs, grav_fix(optional))
+ * are copied to the device. */
+int gi_hmc_create(const gi_hmc_config *cfg, const double *G_dev, const double *dobs_host,
+                  const double *gravfix_host, const double *low_host, const double *high_host,
+                  const double *mwapr_host, const double *wmsq_host, void *stream, gi_hmc **out);
+int gi_hmc_destroy(gi_hmc *h);
+int gi_hmc_set_reg(gi_hmc *h, const gi_reg_params *reg);
+/* set the current position x (hmc.py:271-276) and evaluate U, grad there */
+int gi_hmc_set_state(gi_hmc *h, const double *x_host);
+/* copy out the current position, forward data d = Aw mw (without grav_fix) and mw (any may be NULL) */
+int gi_hmc_get_state(gi_hmc *h, double *x_host, double *d_host, double *mw_host);
+/* current misfit and gradient (potential.py:812-845 return values) */
+int gi_hmc_get_misfit(gi_hmc *h, double *U, double *U_data, double *U_model, double *grad_host);
+
+/* One HMC proposal (hmc.py:85-177) with injected draws: p0_host = randn(M)*Sigma, u = rand().
+ * trace_x_host ((L+1) x M) / trace_U_host (L+1) optionally receive the position and potential
+ * after every gradient evaluation (index 0 = the start point). */
+int gi_hmc_propose(gi_hmc *h, const double *p0_host, int32_t L, double dt, double u,
+                   gi_hmc_result *result, double *trace_x_host, double *trace_U_host);
+/* Same with device-generated draws (Philox4x32-10 + Box-Muller; NOT bit-compatible with numpy's
+ * MT19937 stream): p0 = N(0,1)*sigma from (seed, counter). */
+int gi_hmc_propose_philox(gi_hmc *h, uint64_t seed, uint64_t counter, double sigma, int32_t L,
+                          double dt, gi_hmc_result *result);
+/* Benchmark / warm-up helper: run `nsteps` leapfrog steps (hmc.py:117-152) from the current state
+ * without a Metropolis test; the momentum starts at p0_dev (device, length ld) or zero. */
+int gi_hmc_leapfrog_steps(gi_hmc *h, const double *p0_dev, int32_t nsteps, double dt);
+/* kernels launched by this handle since creation */
+int64_t gi_hmc_launch_count(const gi_hmc *h);
+void *gi_hmc_stream(const gi_hmc *h);
+
+/* ---- wavelet-compressed forward (compressor1D/3D.py) -------------------------------------- */
+/* level-2 db4 periodization DWT of a length-n vector packed like pywt.coeffs_to_array:
+ * out = [cA2 | cD2 | cD1], ncoef = len(out) returned through *ncoef (may be called with
+ * out_dev == NULL to query the size). */
+int gi_dwt_db4_l2_1d(const double *x_dev, int64_t n, double *out_dev, int64_t *ncoef, void *stream);
+/* 3-D variant on a (nz, ny, nx) C-ordered volume, Mallat packing of pywt.coeffs_to_array. */
+int gi_dwt_db4_l2_3d(const double *x_dev, int32_t nz, int32_t ny, int32_t nx, double *out_dev,
+                     int32_t out_shape[3], void *stream);
+/* y = A x for a CSR matrix (int64 indptr[nrows+1], int32 indices, f64 data) */
+int gi_csr_spmv(const int64_t *indptr_dev, const int32_t *indices_dev, const double *data_dev,
+                int64_t nrows, const double *x_dev, double *y_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAVINV_B200_H */
