@@ -1,0 +1,39 @@
+"""Build libgravinv_b200.so (sm_100a) in-tree with nvcc.  Used by __graft_entry__.build()."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = [os.path.join(HERE, "csrc", f) for f in ("assemble.cu", "leapfrog.cu", "wavelet.cu")]
+HDR = [os.path.join(HERE, "csrc", "common.cuh"), os.path.join(ROOT, "include", "gravinv_b200.h")]
+OUT = os.path.join(HERE, "_build", "libgravinv_b200.so")
+
+
+def stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(f) > t for f in SRC + HDR if os.path.exists(f))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return OUT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include")]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [s for s in SRC if os.path.exists(s)] + ["-o", OUT]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,6 @@
+"""Physical constants and unit conversions (same names and values as the reference's
+constants.py:29-44)."""
+SI2MGAL = 100000.0            # constants.py:29
+G_SI = 0.00000000006673       # constants.py:33 (m^3 kg^-1 s^-1; the reference calls it G_SPHERICAL)
+G = 0.00000006673             # constants.py:34 (density in g/cm^3)
+MEAN_EARTH_RADIUS = 6378137.0  # constants.py:44

@@ -1,0 +1,405 @@
+// assemble.cu -- sensitivity-matrix assembly and column weighting on sm_100a.
+//
+// Replaces (reference paths relative to the reference root):
+//   gravmag/_prism.pyx:263-290 gz + :49-50 kernelz + :16-34 safe_atan2/safe_log, driven per prism
+//     by gravmag/prism.py:291-316 _gz                      -> prism_gz_kernel
+//   gravmag/_tesseroid_numba.py:25-157,207-222 engine/scale_nodes/distance_size/split/divisions/
+//     kernelz, driven per tesseroid by gravmag/tesseroid.py:189-232   -> tess_gz_kernel
+//   inversion/potential.py:232-264 sensitivityWeighting     -> colsumsq / weights / scale_columns
+//
+// Layout: G is row-major [nrows][ld]; consecutive threads own consecutive COLUMNS (cells) of one
+// observation row, so every warp store is one contiguous 256 B segment.  The arithmetic keeps the
+// reference's operation order and uses explicit round-to-nearest intrinsics (__dmul_rn/__dadd_rn)
+// so ptxas cannot contract multiply-adds: the closed-form prism kernel cancels ~1e7..1e10 and the
+// reference is plain x86-64 code without FMA.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gi {
+
+// ---------------------------------------------------------------------------------------------
+// prism gz
+// ---------------------------------------------------------------------------------------------
+// _prism.pyx:21 spells pi with more digits than a double holds; this is the same binary64.
+__device__ __constant__ const double kPi = 3.1415926535897931159979634685441851615906;
+
+__device__ __forceinline__ double prism_safe_atan2(double y, double x) {
+    // _prism.pyx:16-26
+    if (y == 0.0) return 0.0;
+    double a = atan2(y, x);
+    if (x < 0.0) {
+        if (y > 0.0) a = __dsub_rn(a, kPi);
+        else if (y < 0.0) a = __dadd_rn(a, kPi);
+    }
+    return a;
+}
+
+__device__ __forceinline__ double prism_safe_log(double x) {
+    // _prism.pyx:28-34
+    return (x == 0.0) ? 0.0 : log(x);
+}
+
+__device__ __forceinline__ double prism_corner(double x, double y, double z) {
+    // r = sqrt(x**2 + y**2 + z**2)  (_prism.pyx:286);  kernelz (_prism.pyx:49-50):
+    // -(x*log(y + r) + y*log(x + r) - z*atan2(x*y, z*r))
+    const double r =
+        __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+    const double t1 = __dmul_rn(x, prism_safe_log(__dadd_rn(y, r)));
+    const double t2 = __dmul_rn(y, prism_safe_log(__dadd_rn(x, r)));
+    const double t3 = __dmul_rn(z, prism_safe_atan2(__dmul_rn(x, y), __dmul_rn(z, r)));
+    return -__dsub_rn(__dadd_rn(t1, t2), t3);
+}
+
+constexpr int kAsmThreads = 128;  // columns per CTA
+constexpr int kAsmRows = 8;       // observation rows per CTA
+
+__global__ void __launch_bounds__(kAsmThreads)
+prism_gz_kernel(const double *__restrict__ xp, const double *__restrict__ yp,
+                const double *__restrict__ zp, int64_t nrows, const double *__restrict__ bounds,
+                int64_t M, double scale, double *__restrict__ G, int64_t ld) {
+    const int64_t col = (int64_t)blockIdx.x * kAsmThreads + threadIdx.x;
+    if (col >= ld) return;
+    const bool live = col < M;
+    double bx[2], by[2], bz[2];
+    if (live) {
+        const double *b = bounds + 6 * col;
+        // corner order of _prism.pyx:272-274: x = [x2, x1], y = [y2, y1], z = [z2, z1]
+        bx[0] = b[1]; bx[1] = b[0];
+        by[0] = b[3]; by[1] = b[2];
+        bz[0] = b[5]; bz[1] = b[4];
+    }
+    for (int64_t tile = blockIdx.y; tile * kAsmRows < nrows; tile += gridDim.y) {
+        const int64_t r0 = tile * kAsmRows;
+        const int nr = (int)min((int64_t)kAsmRows, nrows - r0);
+        for (int rr = 0; rr < nr; ++rr) {
+            const int64_t row = r0 + rr;
+            double acc = 0.0;
+            if (live) {
+                const double ox = __ldg(xp + row), oy = __ldg(yp + row), oz = __ldg(zp + row);
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    // loop nest k (z) outer, j (y), i (x) inner; sign (-1)^(i+j+k)
+                    const int k = c >> 2, j = (c >> 1) & 1, i = c & 1;
+                    const double dz = __dsub_rn(bz[k], oz);
+                    const double dy = __dsub_rn(by[j], oy);
+                    const double dx = __dsub_rn(bx[i], ox);
+                    const double kern = prism_corner(dx, dy, dz);
+                    acc = __dadd_rn(acc, ((i + j + k) & 1) ? -kern : kern);
+                }
+                acc = __dmul_rn(acc, scale);  // prism.py:314-315, after the 8-term sum
+            }
+            G[row * ld + col] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tesseroid gz
+// ---------------------------------------------------------------------------------------------
+constexpr double kEarthRadius = 6378137.0;  // constants.py:44
+constexpr int kStackSize = 100;             // gravmag/tesseroid.py:79
+constexpr double kNodeLo = -0.577350269189625731058868041146;
+constexpr double kNodeHi = 0.577350269189625731058868041146;
+constexpr double kNpPi = 3.141592653589793;  // np.pi
+
+struct TessCell {
+    double w, e, s, n, top, bottom;
+};
+
+__device__ __forceinline__ double tess_leaf(double lon, double coslat, double sinlat, double radius,
+                                            const TessCell &c) {
+    // scale_nodes (_tesseroid_numba.py:75-91) + kernelz (:207-222)
+    const double d2r = kNpPi / 180;
+    const double dlon = __dmul_rn(d2r, __dsub_rn(c.e, c.w));
+    const double dlat = __dmul_rn(d2r, __dsub_rn(c.n, c.s));
+    const double dr = __dsub_rn(c.top, c.bottom);
+    const double nodes[2] = {kNodeLo, kNodeHi};
+    double lonc[2], sinlatc[2], coslatc[2], rc[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        lonc[i] = __dadd_rn(__dmul_rn(__dmul_rn(0.5, dlon), nodes[i]),
+                            __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.e, c.w)));
+        const double latc = __dadd_rn(__dmul_rn(__dmul_rn(0.5, dlat), nodes[i]),
+                                      __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.n, c.s)));
+        sinlatc[i] = sin(latc);
+        coslatc[i] = cos(latc);
+        rc[i] = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(0.5, dr), nodes[i]),
+                                    __dmul_rn(0.5, __dadd_rn(c.top, c.bottom))),
+                          kEarthRadius);
+    }
+    const double scale = __dmul_rn(__dmul_rn(__dmul_rn(dlon, dlat), dr), 0.125);
+    const double r_sqr = __dmul_rn(radius, radius);
+    double result = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double coslon = cos(__dsub_rn(lon, lonc[i]));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double cospsi = __dadd_rn(__dmul_rn(sinlat, sinlatc[j]),
+                                            __dmul_rn(__dmul_rn(coslat, coslatc[j]), coslon));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const double rck2 = __dmul_rn(rc[k], rc[k]);
+                const double l_sqr = __dsub_rn(
+                    __dadd_rn(r_sqr, rck2), __dmul_rn(__dmul_rn(__dmul_rn(2.0, radius), rc[k]), cospsi));
+                const double kappa = __dmul_rn(rck2, coslatc[j]);
+                const double num = __dmul_rn(kappa, __dsub_rn(__dmul_rn(rc[k], cospsi), radius));
+                // l_sqr**1.5 ; pow(x, 1.5) == x*sqrt(x) to within 1 ulp
+                result = __dadd_rn(result, __ddiv_rn(num, __dmul_rn(l_sqr, __dsqrt_rn(l_sqr))));
+            }
+        }
+    }
+    return __dmul_rn(scale, -result);
+}
+
+// Decide the split of one cell (distance_size :94-111 + divisions :135-157).
+// Returns nlon | nlat<<2 | nr<<4, err in *err (0 or -1).
+__device__ __forceinline__ int tess_divisions(double lon, double coslat, double sinlat, double radius,
+                                              const TessCell &c, double ratio, int *err) {
+    const double d2r = kNpPi / 180;
+    const double rt = __dadd_rn(__dmul_rn(0.5, __dadd_rn(c.top, c.bottom)), kEarthRadius);
+    const double lont = __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.w, c.e));
+    const double latt = __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.s, c.n));
+    const double sinlatt = sin(latt), coslatt = cos(latt);
+    const double cospsi = __dadd_rn(__dmul_rn(sinlat, sinlatt),
+                                    __dmul_rn(__dmul_rn(coslat, coslatt), cos(__dsub_rn(lon, lont))));
+    const double distance = __dsqrt_rn(
+        __dsub_rn(__dadd_rn(__dmul_rn(radius, radius), __dmul_rn(rt, rt)),
+                  __dmul_rn(__dmul_rn(__dmul_rn(2.0, radius), rt), cospsi)));
+    const double rtop = __dadd_rn(c.top, kEarthRadius);
+    const double Llon = __dmul_rn(
+        rtop, acos(__dadd_rn(__dmul_rn(sinlatt, sinlatt),
+                             __dmul_rn(__dmul_rn(coslatt, coslatt),
+                                       cos(__dmul_rn(d2r, __dsub_rn(c.e, c.w)))))));
+    const double dn = __dmul_rn(d2r, c.n), ds = __dmul_rn(d2r, c.s);
+    const double Llat = __dmul_rn(
+        rtop, acos(__dadd_rn(__dmul_rn(sin(dn), sin(ds)), __dmul_rn(cos(dn), cos(ds)))));
+    const double Lr = __dsub_rn(c.top, c.bottom);
+    int nlon = 1, nlat = 1, nr = 1, e = 0;
+    if (distance <= __dmul_rn(ratio, Llon)) {
+        if (Llon <= 0.1) e = -1; else nlon = 2;
+    }
+    if (distance <= __dmul_rn(ratio, Llat)) {
+        if (Llat <= 0.1) e = -1; else nlat = 2;
+    }
+    if (distance <= __dmul_rn(ratio, Lr)) {
+        if (Lr <= 1e3) e = -1; else nr = 2;
+    }
+    *err = e;
+    return nlon | (nlat << 2) | (nr << 4);
+}
+
+constexpr int kTessThreads = 128;
+
+__global__ void __launch_bounds__(kTessThreads)
+tess_gz_kernel(const double *__restrict__ lon, const double *__restrict__ sinlat,
+               const double *__restrict__ coslat, const double *__restrict__ radius, int64_t nrows,
+               const double *__restrict__ bounds, int64_t M, double ratio, double scale1,
+               double scale2, double *__restrict__ G, int64_t ld, int32_t *__restrict__ status) {
+    const int64_t col = (int64_t)blockIdx.x * kTessThreads + threadIdx.x;
+    if (col >= ld) return;
+    const bool live = col < M;
+    TessCell root;
+    if (live) {
+        const double *b = bounds + 6 * col;
+        root.w = b[0]; root.e = b[1]; root.s = b[2]; root.n = b[3]; root.top = b[4]; root.bottom = b[5];
+    }
+    TessCell stack[kStackSize];  // local memory; only touched when a cell subdivides
+    int errsum = 0;
+    bool overflow = false;
+    for (int64_t row = blockIdx.y; row < nrows; row += gridDim.y) {
+        double acc = 0.0;
+        if (live) {
+            const double olon = __ldg(lon + row), osin = __ldg(sinlat + row),
+                         ocos = __ldg(coslat + row), orad = __ldg(radius + row);
+            int err;
+            const int div0 = tess_divisions(olon, ocos, osin, orad, root, ratio, &err);
+            errsum += err;
+            if (div0 == (1 | (1 << 2) | (1 << 4))) {
+                acc = tess_leaf(olon, ocos, osin, orad, root);  // fast path: no subdivision
+            } else {
+                // engine (_tesseroid_numba.py:32-71): LIFO stack, children pushed lon-major
+                int top = -1;
+                TessCell cur = root;
+                int div = div0;
+                bool have = true;
+                while (true) {
+                    if (!have) {
+                        if (top < 0) break;
+                        cur = stack[top--];
+                        div = tess_divisions(olon, ocos, osin, orad, cur, ratio, &err);
+                        errsum += err;
+                    }
+                    have = false;
+                    const int nlon = div & 3, nlat = (div >> 2) & 3, nr = (div >> 4) & 3;
+                    const int ncell = nlon * nlat * nr;
+                    if (ncell > 1) {
+                        if (ncell + (top + 1) > kStackSize) {
+                            overflow = true;
+                            acc = nan("");
+                            break;
+                        }
+                        const double dlon = __ddiv_rn(__dsub_rn(cur.e, cur.w), (double)nlon);
+                        const double dlat = __ddiv_rn(__dsub_rn(cur.n, cur.s), (double)nlat);
+                        const double dr = __ddiv_rn(__dsub_rn(cur.top, cur.bottom), (double)nr);
+                        for (int i = 0; i < nlon; ++i)
+                            for (int j = 0; j < nlat; ++j)
+                                for (int k = 0; k < nr; ++k) {
+                                    TessCell c;
+                                    c.w = __dadd_rn(cur.w, __dmul_rn((double)i, dlon));
+                                    c.e = __dadd_rn(cur.w, __dmul_rn((double)(i + 1), dlon));
+                                    c.s = __dadd_rn(cur.s, __dmul_rn((double)j, dlat));
+                                    c.n = __dadd_rn(cur.s, __dmul_rn((double)(j + 1), dlat));
+                                    c.top = __dadd_rn(cur.bottom, __dmul_rn((double)(k + 1), dr));
+                                    c.bottom = __dadd_rn(cur.bottom, __dmul_rn((double)k, dr));
+                                    stack[++top] = c;
+                                }
+                    } else {
+                        acc = __dadd_rn(acc, tess_leaf(olon, ocos, osin, orad, cur));
+                    }
+                }
+            }
+            acc = __dmul_rn(__dmul_rn(acc, scale1), scale2);  // tesseroid.py:430
+        }
+        G[row * ld + col] = acc;
+    }
+    if (errsum != 0) atomicAdd(status, errsum);
+    if (overflow) atomicExch(status + 1, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sensitivity weighting
+// ---------------------------------------------------------------------------------------------
+constexpr int kColThreads = 128;
+
+// One thread per 4 columns, rows summed sequentially in row order (the reference's order,
+// potential.py:241-244), a*a and the add rounded separately.
+__global__ void __launch_bounds__(kColThreads)
+colsumsq_kernel(const double *__restrict__ G, int64_t nrows, int64_t ld, double *__restrict__ out,
+                int accumulate) {
+    const int64_t c4 = ((int64_t)blockIdx.x * kColThreads + threadIdx.x) * 4;
+    if (c4 >= ld) return;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (accumulate) { s0 = out[c4]; s1 = out[c4 + 1]; s2 = out[c4 + 2]; s3 = out[c4 + 3]; }
+    const double *p = G + c4;
+    int64_t r = 0;
+    constexpr int U = 8;
+    for (; r + U <= nrows; r += U) {
+        double a[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) ldg_stream4(p + (r + u) * ld, a[u][0], a[u][1], a[u][2], a[u][3]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s0 = __dadd_rn(s0, __dmul_rn(a[u][0], a[u][0]));
+            s1 = __dadd_rn(s1, __dmul_rn(a[u][1], a[u][1]));
+            s2 = __dadd_rn(s2, __dmul_rn(a[u][2], a[u][2]));
+            s3 = __dadd_rn(s3, __dmul_rn(a[u][3], a[u][3]));
+        }
+    }
+    for (; r < nrows; ++r) {
+        double a0, a1, a2, a3;
+        ldg_stream4(p + r * ld, a0, a1, a2, a3);
+        s0 = __dadd_rn(s0, __dmul_rn(a0, a0));
+        s1 = __dadd_rn(s1, __dmul_rn(a1, a1));
+        s2 = __dadd_rn(s2, __dmul_rn(a2, a2));
+        s3 = __dadd_rn(s3, __dmul_rn(a3, a3));
+    }
+    out[c4] = s0; out[c4 + 1] = s1; out[c4 + 2] = s2; out[c4 + 3] = s3;
+}
+
+__global__ void weights_kernel(const double *__restrict__ sumsq, int64_t M, double wf,
+                               double *__restrict__ wm, double *__restrict__ wminv,
+                               double *__restrict__ wmsq) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    // potential.py:245-253: ADiag = power(ADiagSquare, weightfactor); 1.0/ADiag; ADiag*ADiag
+    const double s = sumsq[i];
+    const double d = (wf == 0.5) ? __dsqrt_rn(s) : pow(s, wf);
+    wm[i] = d;
+    wminv[i] = __ddiv_rn(1.0, d);
+    wmsq[i] = __dmul_rn(d, d);
+}
+
+__global__ void __launch_bounds__(kColThreads)
+scale_columns_kernel(double *__restrict__ G, int64_t nrows, int64_t M, int64_t ld,
+                     const double *__restrict__ cs) {
+    const int64_t c4 = ((int64_t)blockIdx.x * kColThreads + threadIdx.x) * 4;
+    if (c4 >= ld) return;
+    double w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (c4 + k < M) ? cs[c4 + k] : 0.0;
+    for (int64_t r = blockIdx.y; r < nrows; r += gridDim.y) {
+        double *p = G + r * ld + c4;
+        double a0, a1, a2, a3;
+        ldg_stream4(p, a0, a1, a2, a3);
+        stg4(p, __dmul_rn(a0, w[0]), __dmul_rn(a1, w[1]), __dmul_rn(a2, w[2]), __dmul_rn(a3, w[3]));
+    }
+}
+
+}  // namespace gi
+
+using namespace gi;
+
+extern "C" int gi_prism_gz_assemble(const double *xp, const double *yp, const double *zp,
+                                    int64_t nrows, const double *bounds, int64_t M, double scale,
+                                    double *G, int64_t ld, void *stream) {
+    GI_REQUIRE(nrows >= 0 && M >= 0 && ld >= M && ld % 4 == 0, "gi_prism_gz_assemble: bad shape");
+    if (nrows == 0 || ld == 0) return GI_OK;
+    GI_REQUIRE(xp && yp && zp && G && (bounds || M == 0), "gi_prism_gz_assemble: null pointer");
+    dim3 grid((unsigned)ceil_div(ld, kAsmThreads),
+              (unsigned)min((int64_t)65535, ceil_div(nrows, kAsmRows)));
+    prism_gz_kernel<<<grid, kAsmThreads, 0, (cudaStream_t)stream>>>(xp, yp, zp, nrows, bounds, M,
+                                                                    scale, G, ld);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_tess_gz_assemble(const double *lon, const double *sinlat, const double *coslat,
+                                   const double *radius, int64_t nrows, const double *bounds,
+                                   int64_t M, double ratio, double scale1, double scale2, double *G,
+                                   int64_t ld, int32_t *status, void *stream) {
+    GI_REQUIRE(nrows >= 0 && M >= 0 && ld >= M && ld % 4 == 0, "gi_tess_gz_assemble: bad shape");
+    GI_REQUIRE(ratio > 0, "gi_tess_gz_assemble: ratio must be > 0");
+    if (nrows == 0 || ld == 0) return GI_OK;
+    GI_REQUIRE(lon && sinlat && coslat && radius && G && status && (bounds || M == 0),
+               "gi_tess_gz_assemble: null pointer");
+    dim3 grid((unsigned)ceil_div(ld, kTessThreads), (unsigned)min((int64_t)65535, nrows));
+    tess_gz_kernel<<<grid, kTessThreads, 0, (cudaStream_t)stream>>>(
+        lon, sinlat, coslat, radius, nrows, bounds, M, ratio, scale1, scale2, G, ld, status);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_colsumsq(const double *G, int64_t nrows, int64_t M, int64_t ld, double *out,
+                           int accumulate, void *stream) {
+    GI_REQUIRE(nrows >= 0 && M >= 0 && ld >= M && ld % 4 == 0, "gi_colsumsq: bad shape");
+    if (ld == 0) return GI_OK;
+    GI_REQUIRE(G && out, "gi_colsumsq: null pointer");
+    colsumsq_kernel<<<(unsigned)ceil_div(ld / 4, kColThreads), kColThreads, 0,
+                      (cudaStream_t)stream>>>(G, nrows, ld, out, accumulate);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_weights_from_sumsq(const double *sumsq, int64_t M, double wf, double *wm,
+                                     double *wminv, double *wmsq, void *stream) {
+    GI_REQUIRE(M >= 0, "gi_weights_from_sumsq: bad shape");
+    if (M == 0) return GI_OK;
+    GI_REQUIRE(sumsq && wm && wminv && wmsq, "gi_weights_from_sumsq: null pointer");
+    weights_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(sumsq, M, wf, wm,
+                                                                                 wminv, wmsq);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_scale_columns(double *G, int64_t nrows, int64_t M, int64_t ld, const double *cs,
+                                void *stream) {
+    GI_REQUIRE(nrows >= 0 && M >= 0 && ld >= M && ld % 4 == 0, "gi_scale_columns: bad shape");
+    if (nrows == 0 || ld == 0) return GI_OK;
+    GI_REQUIRE(G && cs, "gi_scale_columns: null pointer");
+    dim3 grid((unsigned)ceil_div(ld / 4, kColThreads), (unsigned)min((int64_t)4096, nrows));
+    scale_columns_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(G, nrows, M, ld, cs);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}

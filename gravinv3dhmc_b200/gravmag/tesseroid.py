@@ -1,0 +1,108 @@
+"""Gravity effect gz of tesseroids (spherical prisms) and its sensitivity matrix on the GPU.
+
+Mirror of the reference's gravmag/tesseroid.py `gz` (:421-431) -> `_dispatcher` (:156-186) ->
+`_forward_model` (:189-232) -> numba `engine(kernelz)` (gravmag/_tesseroid_numba.py:25-72):
+2x2x2 Gauss-Legendre quadrature with adaptive subdivision (distance/size ratio 1.6, LIFO stack of
+100 cells).  Same arguments and `(result, kernel2d)` return; raises `AssertionError` for invalid
+input, `OverflowError` when the subdivision stack overflows and emits the same `RuntimeWarning`s.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from .. import _lib
+from ..constants import G, MEAN_EARTH_RADIUS, SI2MGAL
+from ._common import matvec_padded, model_table, to_device
+
+RATIO_G = 1.6     # gravmag/tesseroid.py:77
+STACK_SIZE = 100  # gravmag/tesseroid.py:79
+
+
+def _convert_coords(lon, lat, height):
+    """degrees -> radians, sin/cos of latitude, radius (gravmag/tesseroid.py:109-123)."""
+    lon = np.radians(lon)
+    lat = np.radians(lat)
+    return lon, np.sin(lat), np.cos(lat), MEAN_EARTH_RADIUS + height
+
+
+def _check_table(table):
+    """tesseroid.py:126-153: validate, drop degenerate cells (with the reference's warning)."""
+    if table.shape[0] == 0:
+        return table, 0
+    w, e, s, n, top, bottom = table.T
+    bad = ~((w <= e) & (s <= n) & (top >= bottom))
+    if bad.any():
+        raise AssertionError("Invalid tesseroid dimensions {}".format(list(table[np.argmax(bad)])))
+    tiny = (e - w <= 1e-6) | (n - s <= 1e-6) | (top - bottom <= 1e-3)
+    ndrop = int(tiny.sum())
+    if ndrop:
+        warnings.warn("Encountered tesseroid with dimensions smaller than the numerical threshold "
+                      "(1e-6 degrees or 1e-3 m). Ignoring this tesseroid.", RuntimeWarning)
+        table = table[~tiny]
+    return table, ndrop
+
+
+def assemble(lon, lat, height, table, ratio=RATIO_G, rows=None, device=None, ncols=None):
+    """Device sensitivity matrix [nrows, ld] for an explicit, already validated [M,6] table
+    (w, e, s, n, top, bottom).  `ncols` >= M reserves trailing zero columns."""
+    torch = _lib.require_cuda()
+    lon, lat, height = (np.ascontiguousarray(a, dtype=np.float64) for a in (lon, lat, height))
+    assert lon.shape == lat.shape == height.shape, "Input coordinate arrays must have same shape"
+    assert ratio > 0, "Invalid ratio {}. Must be > 0.".format(ratio)
+    lo, hi = (0, lon.shape[0]) if rows is None else rows
+    table = np.ascontiguousarray(table, dtype=np.float64).reshape(-1, 6)
+    M = table.shape[0]
+    ncols = M if ncols is None else ncols
+    ld = _lib.padded_ld(ncols)
+    n = hi - lo
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    Gd = torch.empty((n, ld), dtype=torch.float64, device=dev)
+    if n == 0 or ld == 0:
+        return Gd, ncols
+    lonr, sinlat, coslat, radius = _convert_coords(lon[lo:hi], lat[lo:hi], height[lo:hi])
+    a_d = [to_device(a, torch, dev) for a in (lonr, sinlat, coslat, radius)]
+    tab_d = to_device(table if M else np.zeros((1, 6)), torch, dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    _lib.check(L.gi_tess_gz_assemble(_lib.ptr(a_d[0]), _lib.ptr(a_d[1]), _lib.ptr(a_d[2]),
+                                     _lib.ptr(a_d[3]), n, _lib.ptr(tab_d), M, float(ratio),
+                                     SI2MGAL, G, _lib.ptr(Gd), ld, _lib.ptr(status),
+                                     _lib.stream_ptr()), "gi_tess_gz_assemble")
+    err, overflow = (int(v) for v in status.cpu())
+    if overflow:
+        raise OverflowError("tesseroid subdivision stack overflow (STACK_SIZE = 100)")
+    if err != 0:  # tesseroid.py:228-229
+        warnings.warn("Stopped dividing a tesseroid because it's dimensions would be below the "
+                      "minimum numerical threshold (1e-6 degrees or 1e-3 m). Will compute without "
+                      "division. Cannot guarantee the accuracy of the solution.", RuntimeWarning)
+    return Gd, ncols
+
+
+def gz(lon, lat, height, model, dens=None, ratio=RATIO_G, njobs=1, pool=None, device_out=False):
+    """Calculate gz (mGal, density in g/cm^3) of a tesseroid model and the kernel matrix.
+
+    `kernel2d` has one column per non-masked tesseroid; degenerate tesseroids are skipped, which
+    (as in the reference, tesseroid.py:98-105 vs :218-231) leaves that many trailing zero columns."""
+    assert njobs > 0, "Invalid number of jobs {}. Must be > 0.".format(njobs)
+    if njobs == 1:
+        assert pool is None, "njobs should be number of processes in the pool"
+    table, rho = model_table(model, dens, "tesseroid")
+    ncols = table.shape[0]
+    if ncols:
+        keep = ~((table[:, 1] - table[:, 0] <= 1e-6) | (table[:, 3] - table[:, 2] <= 1e-6)
+                 | (table[:, 4] - table[:, 5] <= 1e-3))
+        table, _ = _check_table(table)
+        if rho is not None:
+            rho = rho[keep]
+    Gd, _ = assemble(lon, lat, height, table, ratio=ratio, ncols=ncols)
+    torch = _lib.require_cuda()
+    M = table.shape[0]
+    if M and rho is not None and np.any(rho != 0):
+        res = matvec_padded(Gd, M, to_device(rho, torch, Gd.device), torch)
+    else:
+        res = torch.zeros(Gd.shape[0], dtype=torch.float64, device=Gd.device)
+    if device_out:
+        return res, Gd
+    return res.cpu().numpy(), Gd[:, :ncols].cpu().numpy()

@@ -27,7 +27,8 @@
  *     copies asynchronous).  No torch types cross this boundary.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - all arithmetic is IEEE binary64; matrices are row-major with leading dimension `ld`
- *     (in doubles, a multiple of 4; columns [M, ld) must be zero).
+ *     (in doubles, a multiple of 4; columns [M, ld) must be zero).  Every device "M-vector"
+ *     (x, mw, p, grad, low, high, wm ...) is allocated with ld entries, entries [M, ld) zero.
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
  *     GI_ERR_CUDA.
  */
@@ -82,12 +83,6 @@ int gi_tess_gz_assemble(const double *lon_dev, const double *sinlat_dev, const d
                         int64_t M, double ratio, double scale1, double scale2, double *G_dev,
                         int64_t ld, int32_t *status_dev, void *stream);
 
-/* Forward field of a density model without storing G (prism.gz `result`, prism.py:291-316):
- * res[l] = scale * sum_c dens[c] * gz(l, c), accumulated corner by corner in reference order. */
-int gi_prism_gz_forward(const double *xp_dev, const double *yp_dev, const double *zp_dev,
-                        int64_t nrows, const double *bounds_dev, const double *dens_dev, int64_t M,
-                        double scale, double *res_dev, void *stream);
-
 /* ---- sensitivity weighting (potential.py:232-264) ---------------------------------------- */
 /* out[c] (+)= sum_l G[l][c]^2, rows summed sequentially in row order. */
 int gi_colsumsq(const double *G_dev, int64_t nrows, int64_t M, int64_t ld, double *out_dev,
@@ -114,9 +109,10 @@ int gi_gemv_fwd(gi_plan *plan, const double *G_dev, const double *x_dev, double 
 /* sums_dev[0] = sum_l (d[l] + fix[l])   (fix_dev may be NULL) */
 int gi_data_sum(gi_plan *plan, const double *d_dev, const double *fix_dev, double *sums_dev,
                 void *stream);
-/* r[l] = (d[l] + fix[l] - mean) - dobs_c[l];  sums_dev[1] = sum r^2.  mean = *mean_dev. */
+/* r[l] = (d[l] + fix[l] - mean) - dobs_c[l] with mean = sums_dev[0] / n_total (sums_dev[0] is
+ * the sum over ALL ranks' rows, n_total the global observation count);  sums_dev[1] = sum r^2. */
 int gi_residual(gi_plan *plan, const double *d_dev, const double *fix_dev,
-                const double *dobs_c_dev, const double *mean_dev, double *r_dev, double *sums_dev,
+                const double *dobs_c_dev, int64_t n_total, double *r_dev, double *sums_dev,
                 void *stream);
 /* g = G^T r (no factor 2; the caller's update applies it).  Deterministic. */
 int gi_gemv_adj(gi_plan *plan, const double *G_dev, const double *r_dev, double *g_dev,
@@ -201,6 +197,13 @@ int gi_dwt_db4_l2_1d(const double *x_dev, int64_t n, double *out_dev, int64_t *n
 /* 3-D variant on a (nz, ny, nx) C-ordered volume, Mallat packing of pywt.coeffs_to_array. */
 int gi_dwt_db4_l2_3d(const double *x_dev, int32_t nz, int32_t ny, int32_t nx, double *out_dev,
                      int32_t out_shape[3], void *stream);
+/* batched variants: `batch` vectors/volumes (<= 65535) with strides x_bs / out_bs in doubles
+ * (used to transform many kernel rows at once, compressor*.kernelcompressor) */
+int gi_dwt_db4_l2_1d_batch(const double *x_dev, int64_t batch, int64_t x_bs, int64_t n,
+                           double *out_dev, int64_t out_bs, int64_t *ncoef, void *stream);
+int gi_dwt_db4_l2_3d_batch(const double *x_dev, int64_t batch, int64_t x_bs, int32_t nz, int32_t ny,
+                           int32_t nx, double *out_dev, int64_t out_bs, int32_t out_shape[3],
+                           void *stream);
 /* y = A x for a CSR matrix (int64 indptr[nrows+1], int32 indices, f64 data) */
 int gi_csr_spmv(const int64_t *indptr_dev, const int32_t *indices_dev, const double *data_dev,
                 int64_t nrows, const double *x_dev, double *y_dev, void *stream);
