@@ -55,7 +55,9 @@ def matvec_padded(Gpad, M, vec, torch):
     N, ld = Gpad.shape
     x = torch.zeros(ld, dtype=torch.float64, device=Gpad.device)
     x[:M] = vec
-    d = torch.empty(N, dtype=torch.float64, device=Gpad.device)
+    d = torch.zeros(N, dtype=torch.float64, device=Gpad.device)
+    if N == 0 or M == 0:
+        return d
     import ctypes as C
 
     plan = C.c_void_p()
