@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GravInv3DHMC hot path on B200.
+
+Metric (BASELINE.json): HMC leapfrog steps/s (+ GEMV HBM GB/s, G-assembly Mpairs/s) on the
+synthetic Cartesian grid c5 = 64x128x128 voxels (1 048 576) x 16 384 observations, FP64 G
+(137.4 GB), row-sharded over 1/2/4/8 B200 (strong scaling: the total problem is fixed).
+
+One "step" = one leapfrog iteration of inversion/hmc.py:117-152 for every chain of the batch:
+d = Aw mw, residual, g = Aw^T r, regulariser gradient, momentum/position update, clamp-and-flip.
+
+    python bench.py [--gpus N --steps K --warmup W]          # our arm (CUDA through the C ABI)
+    python bench.py --impl reference ...                     # the reference's CPU path (numpy), port
+
+Prints ONE JSON line on rank 0.  `value` is device-timed with everything resident in HBM; `e2e`
+goes through the public sampler call (`HamitonianMC._leapfrog`) with host momentum in and the host
+state out inside the timed region.  `roofline` is the dominant kernel against the measured HBM
+peak; `cpu_baseline` is the oracle port of the reference path on the host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nz, ny, nx), cell size [m], observations per side
+    "c5": ((64, 128, 128), 100.0, 128),       # BASELINE.json configs[4]
+    "c5_half": ((64, 128, 128), 100.0, 90),   # 8100 obs (68 GB) -- for boxes with less free HBM
+    "mid": ((32, 64, 64), 100.0, 64),         # 131 072 voxels x 4096 obs (4.3 GB)
+    "tiny": ((16, 32, 32), 100.0, 32),        # 16 384 voxels x 1024 obs
+}
+HMC = dict(delta=0.01, Sigma=0.001, Lrange=[5, 20], RegulFactor=1.0, regularization="Damping",
+           beta=0.001, rhomin=0.0, rhomax=1.0, init=0.001, seed=100)
+
+
+def workload_geometry(name):
+    (nz, ny, nx), h, side = WORKLOADS[name]
+    mrange = (0.0, nx * h, 0.0, ny * h, 0.0, nz * h)
+    xs = np.linspace(h / 2, nx * h - h / 2, side)
+    ys = np.linspace(h / 2, ny * h - h / 2, side)
+    X, Y = np.meshgrid(xs, ys)
+    obs = (X.ravel().copy(), Y.ravel().copy(), np.full(X.size, -1.0))
+    rho = np.zeros((nz, ny, nx))
+    rho[nz // 4: nz // 2, 3 * ny // 8: 5 * ny // 8, 3 * nx // 8: 5 * nx // 8] = 1.0
+    return mrange, (h, h, h), obs, rho.ravel()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi poll of SM clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [l.split(",") for l in open(self.f.name).read().strip().splitlines() if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]  # the loaded half of the samples
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's leapfrog (numpy dgemv, 1 BLAS thread per chain, independent chain
+# processes like `mpiexec -n K`) on a bounded row sample of the same workload.
+# ---------------------------------------------------------------------------------------------
+_CPU_SHARED = {}  # the row sample, inherited by the forked chain workers (never pickled)
+
+
+def _cpu_worker(args):
+    steps, seed = args
+    Aw, wm, dobs, mshape = (_CPU_SHARED[k] for k in ("Aw", "wm", "dobs", "mshape"))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)  # inversion/hmc.py:18-19 pins BLAS to one thread per chain
+    except Exception:
+        pass
+    from oracle import oracle_np as onp
+    M = wm.size
+    model = onp.OracleModel(Aw, wm, dobs, mshape)
+    rs = np.random.RandomState(seed)
+    low, high = wm * HMC["rhomin"], wm * HMC["rhomax"]
+    x0 = wm * HMC["init"]
+    p0 = rs.randn(M) * HMC["Sigma"]
+    t0 = time.perf_counter()
+    onp.leapfrog(model, x0, HMC["delta"], steps, HMC["RegulFactor"], p0, 0.5, x0, low, high,
+                 "mandatory", 1000, HMC["regularization"], HMC["beta"])
+    return steps, time.perf_counter() - t0
+
+
+def cpu_reference_arm(workload, sample_rows, steps, cores=None):
+    """returns dict(value=steps/s scaled to the full row count, ...) for the oracle port."""
+    from oracle import oracle_np as onp
+    import multiprocessing as mp
+
+    onp.build()
+    cores = cores or os.cpu_count() or 1
+    mrange, mspacing, obs, rho = workload_geometry(workload)
+    mesh = onp.OracleMesh(mrange, mspacing)
+    tab, _ = mesh.active_bounds()
+    N = obs[0].size
+    sample_rows = min(sample_rows, N)
+    idx = np.linspace(0, N - 1, sample_rows).astype(np.int64)
+    t0 = time.perf_counter()
+    _, A = onp.prism_gz(obs[0][idx], obs[1][idx], obs[2][idx], tab, threads=cores)
+    t_asm = time.perf_counter() - t0
+    sumsq = np.einsum("ij,ij->j", A, A)
+    wm = np.sqrt(sumsq)
+    A *= (1.0 / wm)[None, :]
+    dobs = A @ (wm * rho)
+    _CPU_SHARED.update(Aw=A, wm=wm, dobs=dobs, mshape=mesh.shape)
+    jobs = [(steps, 100 + c) for c in range(cores)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        out = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    # every worker streams the sample (2 passes per gradient evaluation, steps+1 evaluations)
+    rate_sample = sum(s / t for s, t in out)            # chain-steps/s on the row sample
+    value = rate_sample * sample_rows / N               # scaled to the full observation count
+    return dict(value=value, unit="leapfrog steps/s", cores=cores, kind="port",
+                sample=("%d of %d observation rows x %d voxels (%.2f GB Aw), %d independent "
+                        "single-BLAS-thread chains x %d leapfrog steps (oracle port of "
+                        "inversion/hmc.py:_leapfrog + potential.py:misfit_and_grad, numpy dgemv); "
+                        "rate scaled by rows/N" % (sample_rows, N, tab.shape[0], A.nbytes / 1e9,
+                                                  cores, steps)),
+                assembly_mpairs_per_s=A.size / t_asm / 1e6, wall_s=wall,
+                gbytes_per_s=rate_sample * 2 * A.nbytes / 1e9)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from gravinv3dhmc_b200 import _lib
+    from gravinv3dhmc_b200.inversion import hmc, potential, sharded
+    from gravinv3dhmc_b200.inversion._engine import reg_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gravinv3dhmc_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    if args.gpus != world and rank == 0:
+        print("bench.py: --gpus %d but WORLD_SIZE=%d; using %d" % (args.gpus, world, world),
+              file=sys.stderr)
+    lib = _lib.lib()
+
+    mrange, mspacing, obs, rho = workload_geometry(args.workload)
+    N = obs[0].size
+    nz, ny, nx = WORKLOADS[args.workload][0]
+    M = nz * ny * nx
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- setup: assemble this rank's rows, weight in place (timed for the Mpairs/s line) ----
+    free, total = torch.cuda.mem_get_info()
+    lo, hi = potential.split_rows(N, world)[rank]
+    need = (hi - lo) * _lib.padded_ld(M) * 8
+    if need > free - (3 << 30):
+        raise SystemExit("bench.py: shard needs %.1f GB, only %.1f GB free on %s"
+                         % (need / 1e9, free / 1e9, torch.cuda.get_device_name(dev)))
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    e0.record()
+    model = potential.GravMagModule(np.zeros(N), mrange, mspacing, obs, coordinate="cartesian",
+                                    shard=(rank, world) if world > 1 else None, group=group,
+                                    verbose=False, timing=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t_asm = model.timing["assemble_ms"] * 1e-3
+    t_wgt = model.timing["weight_ms"] * 1e-3
+    n_local = hi - lo
+    # synthetic observations: dobs = A rho_true + 2% noise
+    wm = model.Wm.diagonal()
+    d_local = model.forward_local(wm * rho)
+    if world > 1:
+        if N % world:
+            raise SystemExit("bench.py: the observation count must divide by the GPU count")
+        parts = [torch.zeros_like(d_local) for _ in range(world)]
+        dist.all_gather(parts, d_local, group=group)
+        d_full = torch.cat(parts).cpu().numpy()
+    else:
+        d_full = d_local.cpu().numpy()
+    noise = np.random.default_rng(12345).normal(0.0, 0.02 * np.abs(d_full).max(), N)
+    dobs = d_full + noise
+    model.set_dobs(dobs)
+
+    b = np.zeros((M, 2))
+    b[:, 0], b[:, 1] = HMC["rhomin"], HMC["rhomax"]
+    chain = hmc.setup_chain(model, HMC["delta"], HMC["Lrange"], np.full(M, HMC["init"]),
+                            np.full(M, HMC["init"]), b, "mandatory", 1000, dobs, "Fixed", 0.8,
+                            HMC["RegulFactor"], HMC["regularization"], HMC["beta"], HMC["seed"],
+                            HMC["Sigma"], myrank=0, quiet=True)
+    alpha, dt = HMC["RegulFactor"], HMC["delta"]
+    rs = np.random.RandomState(HMC["seed"])
+    p0 = torch.zeros(model.ld, dtype=torch.float64, device=dev)
+    p0[:M] = torch.as_tensor(rs.randn(M) * HMC["Sigma"], device=dev)
+    x0 = chain.initial_model
+
+    launches = 0
+    # ---- the timed region: K leapfrog steps, everything resident in HBM ----
+    if world == 1:
+        chain._ensure_handle(alpha)
+        chain._sync_state(x0)
+
+        def run_steps(k):
+            _lib.check(lib.gi_hmc_leapfrog_steps(chain._h, _lib.ptr(p0), int(k), float(dt)),
+                       "gi_hmc_leapfrog_steps")
+
+        def launch_count():
+            return int(lib.gi_hmc_launch_count(chain._h))
+    else:
+        reg = reg_params(HMC["regularization"], "mandatory", model.mshape, alpha, HMC["beta"], 1000)
+        st = sharded._ShardState(chain, alpha)
+        sharded._set_state(st, chain, reg, x0)
+
+        def run_steps(k):
+            st.p.copy_(p0)
+            xin, outs = st.x_cur, (st.xa, st.xb)
+            # k gradient evaluations + fused updates (hmc.py:117-152)
+            for i in range(k):
+                xout = outs[i & 1]
+                sharded._grad_eval(st, chain, reg, xin, xin, xout, xout, None, dt, dt, 1)
+                xin = xout
+
+        def launch_count():
+            return int(st.eng.launches)
+
+    run_steps(args.warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=group)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    run_steps(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=group)
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        ms = float(t[0])
+    steps_per_s = args.steps / (ms * 1e-3)
+
+    # ---- per-kernel roofline: the two streaming passes, timed alone with events ----
+    eng = model.engine()
+    xv = eng.vec(x0)
+    s = _lib.stream_ptr()
+
+    def time_kernel(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b_ = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) * 1e-3 / reps
+
+    reps = max(3, min(args.steps, 10))
+    t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemv_fwd(eng.plan, _lib.ptr(eng.Aw), _lib.ptr(xv),
+                                                           _lib.ptr(eng.d), s)), reps)
+    t_adj = time_kernel(lambda: _lib.check(lib.gi_gemv_adj(eng.plan, _lib.ptr(eng.Aw),
+                                                           _lib.ptr(eng.r), _lib.ptr(eng.g), s)), reps)
+    bytes_pass = 8.0 * n_local * M  # algorithmic: every element of the shard once per pass
+    peak, peak_src = peaks()
+    kern = {"gemv_fwd": {"ms": t_fwd * 1e3, "GBps": bytes_pass / t_fwd / 1e9},
+            "gemv_adj": {"ms": t_adj * 1e3, "GBps": bytes_pass / t_adj / 1e9}}
+    dom = "gemv_adj" if t_adj >= t_fwd else "gemv_fwd"
+    achieved = kern[dom]["GBps"]
+    if world > 1:
+        t = torch.tensor([achieved], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        achieved = float(t[0])
+
+    # ---- e2e: the public per-proposal call with host buffers (momentum in, state out) ----
+    e2e = None
+    if world == 1:
+        np.random.seed(HMC["seed"])
+        x = x0
+        done, nprop = 0, 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while done < args.steps:
+            L = min(np.random.randint(HMC["Lrange"][0], HMC["Lrange"][1] + 1), args.steps - done) or 1
+            x, U, dsyn, acc, Ud, Um = chain._leapfrog(x, dt, L, alpha)
+            done += L
+            nprop += 1
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        # per proposal: p0 (8M bytes) + u in; result struct + x (8M) + d (8N) out on accept
+        e2e = {"value": done / t_e2e, "unit": "leapfrog steps/s",
+               "h2d_bytes_per_step": int(nprop * (8 * M + 8) / done),
+               "d2h_bytes_per_step": int(nprop * (8 * M + 8 * N + 80) / done),
+               "proposals": nprop, "api": "HamitonianMC._leapfrog -> gi_hmc_propose"}
+    else:
+        np.random.seed(HMC["seed"])
+        x = x0
+        done, nprop = 0, 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        t0 = time.perf_counter()
+        while done < args.steps:
+            L = min(np.random.randint(HMC["Lrange"][0], HMC["Lrange"][1] + 1), args.steps - done) or 1
+            x, U, dsyn, acc, Ud, Um = chain._leapfrog(x, dt, L, alpha)
+            done += L
+            nprop += 1
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        t_e2e = time.perf_counter() - t0
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        e2e = {"value": done / float(t[0]), "unit": "leapfrog steps/s",
+               "h2d_bytes_per_step": int(nprop * (8 * M + 8) / done),
+               "d2h_bytes_per_step": int(nprop * (8 * M + 8 * n_local + 64) / done),
+               "proposals": nprop, "api": "HamitonianMC._leapfrog (row-sharded, NCCL all-reduce)"}
+
+    asm_t = torch.tensor([t_asm, t_wgt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(asm_t, op=dist.ReduceOp.MAX, group=group)
+    t_asm, t_wgt = (float(v) for v in asm_t)
+
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_arm(args.workload, args.cpu_rows, args.cpu_steps)
+        out = {
+            "metric": "hmc_leapfrog_steps_per_s", "value": steps_per_s, "unit": "leapfrog steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, FP64 Aw "
+                                   "%.1f GB row-sharded over %d GPU(s), Damping, 1 chain; inputs "
+                                   "(%.1f GB per GPU per pass) exceed the 126 MB L2, no flush needed"
+                                   % (args.workload, nz, ny, nx, M, N, 8e-9 * N * M, world,
+                                      8e-9 * n_local * M),
+                       "voxels": M, "observations": N, "chains": 1, "parallelism": "rows%d" % world},
+            "gemv_hbm_GBps": (2 * bytes_pass * world) * steps_per_s / 1e9,
+            "assembly": {"mpairs_per_s": N * M / t_asm / 1e6, "seconds": t_asm,
+                         "weighting_seconds": t_wgt},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernels": kern,
+                         "frac_of_nominal_8TBps": achieved / 8000.0},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier(group=group)
+        dist.destroy_process_group()
+    return out
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    (nz, ny, nx), _, side = WORKLOADS[args.workload]
+    M, N = nz * ny * nx, side * side
+    steps = max(args.steps, 1)
+    best = None
+    for _ in range(max(1, min(args.warmup, 1))):  # one untimed pass warms the page cache / BLAS
+        pass
+    cpu = cpu_reference_arm(args.workload, args.cpu_rows, min(steps, args.cpu_steps))
+    best = cpu
+    v = best["value"]
+    return {"impl": "reference", "metric": "hmc_leapfrog_steps_per_s", "value": v,
+            "unit": "leapfrog steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, Damping; CPU "
+                                   "reference path on a row sample" % (args.workload, nz, ny, nx, M, N),
+                       "voxels": M, "observations": N, "chains": best["cores"]},
+            "cpu_baseline": best,
+            "e2e": {"value": v, "unit": "leapfrog steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-rows", type=int, default=128, help="observation rows of the CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=8, help="leapfrog steps per CPU chain")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    out = reference_arm(args) if args.impl == "reference" else gpu_arm(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -246,13 +246,15 @@ class HamitonianMC:
             sys.stdout.flush()
 
 
-def HMCSample(model, nsamples, ndraws, delta, Lrange, initial_model, aprior_model, boundaries,
-              constraint, log_factor, dobs, adaptiveRegul, RegulRate, RegulFactor, regularization,
-              beta, seed, Sigma, nbest=100, myrank=0, save_folder="mychain", plotsamples=False,
-              im=[0, 0], rng="numpy", quiet=False, max_proposals=None):
-    """HMC sampling function -- hmc.py:358-403.  `adaptiveRegul`, `RegulRate` and `nbest` are
-    accepted and (as in the reference's sampler) unused.  Returns the chain object (extension; the
-    reference returns None)."""
+def setup_chain(model, delta, Lrange, initial_model, aprior_model, boundaries, constraint,
+                log_factor, dobs, adaptiveRegul, RegulRate, RegulFactor, regularization, beta, seed,
+                Sigma, nbest=100, myrank=0, save_folder="mychain", plotsamples=False, im=[0, 0],
+                rng="numpy", quiet=False):
+    """The chain object of hmc.py:358-401 (everything HMCSample does before `chain.sample`)."""
+    if constraint not in _lib.CONSTRAINTS:
+        raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
+    if regularization not in _lib.REG_KINDS:
+        raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
     chain = HamitonianMC(model)
     chain.myrank = myrank
     chain.save_folder = save_folder + str(myrank)
@@ -283,9 +285,18 @@ def HMCSample(model, nsamples, ndraws, delta, Lrange, initial_model, aprior_mode
     chain.plotsamples = plotsamples
     chain.rng = rng
     chain.quiet = quiet
-    if constraint not in _lib.CONSTRAINTS:
-        raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
-    if regularization not in _lib.REG_KINDS:
-        raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
+    return chain
+
+
+def HMCSample(model, nsamples, ndraws, delta, Lrange, initial_model, aprior_model, boundaries,
+              constraint, log_factor, dobs, adaptiveRegul, RegulRate, RegulFactor, regularization,
+              beta, seed, Sigma, nbest=100, myrank=0, save_folder="mychain", plotsamples=False,
+              im=[0, 0], rng="numpy", quiet=False, max_proposals=None):
+    """HMC sampling function -- hmc.py:358-403.  `adaptiveRegul`, `RegulRate` and `nbest` are
+    accepted and (as in the reference's sampler) unused.  Returns the chain object (extension; the
+    reference returns None)."""
+    chain = setup_chain(model, delta, Lrange, initial_model, aprior_model, boundaries, constraint,
+                        log_factor, dobs, adaptiveRegul, RegulRate, RegulFactor, regularization,
+                        beta, seed, Sigma, nbest, myrank, save_folder, plotsamples, im, rng, quiet)
     chain.sample(nsamples, ndraws, max_proposals=max_proposals)
     return chain

@@ -37,6 +37,8 @@ class GravMagModule:
         shard = kwargs.pop("shard", None)
         self.group = kwargs.pop("group", None)
         self.verbose = kwargs.pop("verbose", True)
+        timing = kwargs.pop("timing", False)  # extension: CUDA-event times of the setup kernels
+        self.timing = {}
         self.dobs = np.asarray(dobs, dtype=np.float64)
         self.fixed = fixed
         self.grav_fix = grav_fix
@@ -78,6 +80,7 @@ class GravMagModule:
 
         self._say("Start of calculate kernel")
         start = time.time()
+        ev = self._events(timing)
         table = mesh.bounds_table()
         if spherical:
             ncols = table.shape[0]
@@ -87,6 +90,7 @@ class GravMagModule:
         else:
             Apad, M = prism.assemble(self.lonobs, self.latobs, self.heightobs, table,
                                      rows=self.rows)
+        self._lap(ev, "assemble_ms")
         self._say("kernel.shape ({}, {})".format(n_total, M))
         self._say("End of calculate kernel:%.6f s" % (time.time() - start))
         self.M, self.ld = M, int(Apad.shape[1])
@@ -96,7 +100,9 @@ class GravMagModule:
         self._say("Start to weight kernel")
         start = time.time()
         self.Aw_pad = Apad
+        ev = self._events(timing)
         self.sensitivityWeighting()
+        self._lap(ev, "weight_ms")
         self._say("End of weighting kernel: %.6f s" % (time.time() - start))
 
         self._engine = None
@@ -111,6 +117,37 @@ class GravMagModule:
     def _say(self, msg):
         if self.verbose:
             print(msg)
+
+    @staticmethod
+    def _events(enabled):
+        if not enabled:
+            return None
+        torch = _lib.require_cuda()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _lap(self, start, key):
+        if start is None:
+            return
+        torch = _lib.require_cuda()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        e.synchronize()
+        self.timing[key] = start.elapsed_time(e)
+
+    def set_dobs(self, dobs):
+        """replace the observed data (extension; e.g. synthetic data generated from this kernel)"""
+        self.dobs = np.asarray(dobs, dtype=np.float64)
+        self._engine = None
+
+    def forward_local(self, mw):
+        """device vector Aw[rows] @ mw for this rank's observation rows (extension)"""
+        eng = self.engine()
+        mw_d = eng.vec(mw)
+        _lib.check(eng.L.gi_gemv_fwd(eng.plan, _lib.ptr(eng.Aw), _lib.ptr(mw_d), _lib.ptr(eng.d),
+                                     _lib.stream_ptr()), "gi_gemv_fwd")
+        return eng.d.clone()
 
     # ------------------------------------------------------------------ weighting
     def sensitivityWeighting(self):
