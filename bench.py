@@ -56,6 +56,12 @@ def workload_geometry(name):
     return mrange, (h, h, h), obs, rho.ravel()
 
 
+# FP64 pipe peak of this pool's B200s: DMMA m8n8k4 and DFMA both saturate at 37.1 TFLOP/s
+# (tools/probes/fp64_peak.cu, profiles/r01_fp64_peak_probe.txt); MEASURED_PEAKS.json has no FP64 entry.
+FP64_PEAK_TFLOPS = 37.1
+FP64_PEAK_SRC = "measured here (tools/probes/fp64_peak.cu: DMMA m8n8k4 = DFMA = 37.1 TFLOP/s FP64)"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,8 +266,29 @@ def gpu_arm(args):
     x0 = chain.initial_model
 
     launches = 0
-    # ---- the timed region: K leapfrog steps, everything resident in HBM ----
-    if world == 1:
+    nch = args.chains
+    bt = None
+    # ---- the timed region: K leapfrog steps of every chain, everything resident in HBM ----
+    if world == 1 and nch > 1:
+        from gravinv3dhmc_b200.inversion import batched
+        bt = batched.HMCBatch(model, nch, HMC["delta"], HMC["Lrange"], np.full(M, HMC["init"]),
+                              np.full(M, HMC["init"]), b, "mandatory", 1000, dobs, HMC["RegulFactor"],
+                              HMC["regularization"], HMC["beta"], HMC["seed"], HMC["Sigma"],
+                              save_folder=os.path.join(tempfile.gettempdir(), "gi_bench_chain"),
+                              quiet=True)
+        cp = int(lib.gi_hmcb_padded_chains(bt._h))
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(HMC["seed"])
+        p0b = torch.zeros((cp, model.ld), dtype=torch.float64, device=dev)
+        p0b[:nch, :M] = torch.randn((nch, M), dtype=torch.float64, device=dev, generator=gen) * HMC["Sigma"]
+
+        def run_steps(k):
+            _lib.check(lib.gi_hmcb_leapfrog_steps(bt._h, _lib.ptr(p0b), int(k), float(dt)),
+                       "gi_hmcb_leapfrog_steps")
+
+        def launch_count():
+            return int(lib.gi_hmcb_launch_count(bt._h))
+    elif world == 1:
         chain._ensure_handle(alpha)
         chain._sync_state(x0)
 
@@ -272,6 +299,7 @@ def gpu_arm(args):
         def launch_count():
             return int(lib.gi_hmc_launch_count(chain._h))
     else:
+        nch = 1
         reg = reg_params(HMC["regularization"], "mandatory", model.mshape, alpha, HMC["beta"], 1000)
         st = sharded._ShardState(chain, alpha)
         sharded._set_state(st, chain, reg, x0)
@@ -311,11 +339,10 @@ def gpu_arm(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         ms = float(t[0])
-    steps_per_s = args.steps / (ms * 1e-3)
+    steps_per_s = nch * args.steps / (ms * 1e-3)  # chain-steps per second over the whole job
 
-    # ---- per-kernel roofline: the two streaming passes, timed alone with events ----
+    # ---- per-kernel roofline: the two big passes, timed alone with events ----
     eng = model.engine()
-    xv = eng.vec(x0)
     s = _lib.stream_ptr()
 
     def time_kernel(fn, reps):
@@ -331,16 +358,44 @@ def gpu_arm(args):
         return a.elapsed_time(b_) * 1e-3 / reps
 
     reps = max(3, min(args.steps, 10))
-    t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemv_fwd(eng.plan, _lib.ptr(eng.Aw), _lib.ptr(xv),
-                                                           _lib.ptr(eng.d), s)), reps)
-    t_adj = time_kernel(lambda: _lib.check(lib.gi_gemv_adj(eng.plan, _lib.ptr(eng.Aw),
-                                                           _lib.ptr(eng.r), _lib.ptr(eng.g), s)), reps)
+    hbm_peak, hbm_src = peaks()
     bytes_pass = 8.0 * n_local * M  # algorithmic: every element of the shard once per pass
-    peak, peak_src = peaks()
-    kern = {"gemv_fwd": {"ms": t_fwd * 1e3, "GBps": bytes_pass / t_fwd / 1e9},
-            "gemv_adj": {"ms": t_adj * 1e3, "GBps": bytes_pass / t_adj / 1e9}}
-    dom = "gemv_adj" if t_adj >= t_fwd else "gemv_fwd"
-    achieved = kern[dom]["GBps"]
+    if nch > 1:
+        plan = C.c_void_p()
+        _lib.check(lib.gi_plan_create(n_local, M, model.ld, nch, C.byref(plan)), "gi_plan_create")
+        cpi, npad = C.c_int32(), C.c_int64()
+        _lib.check(lib.gi_plan_batch_info(plan, C.byref(cpi), C.byref(npad)))
+        f64 = dict(dtype=torch.float64, device=dev)
+        Xb = torch.zeros((cpi.value, model.ld), **f64)
+        Xb[:nch, :M] = torch.as_tensor(x0, device=dev)
+        Db = torch.zeros((cpi.value, n_local), **f64)
+        Rb = torch.zeros((cpi.value, npad.value), **f64)
+        Rb[:nch, :n_local] = 1e-3
+        Gb = torch.zeros((cpi.value, model.ld), **f64)
+        t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemm_fwd(plan, _lib.ptr(eng.Aw), _lib.ptr(Xb),
+                                                               _lib.ptr(Db), s)), reps)
+        t_adj = time_kernel(lambda: _lib.check(lib.gi_gemm_adj(plan, _lib.ptr(eng.Aw), _lib.ptr(Rb),
+                                                               _lib.ptr(Gb), s)), reps)
+        lib.gi_plan_destroy(plan)
+        del Xb, Db, Rb, Gb
+        flops_pass = 2.0 * n_local * M * nch  # algorithmic: one FMA per (row, voxel, chain)
+        kern = {"gemm_fwd": {"ms": t_fwd * 1e3, "TFLOPs": flops_pass / t_fwd / 1e12,
+                             "GBps": bytes_pass / t_fwd / 1e9},
+                "gemm_adj": {"ms": t_adj * 1e3, "TFLOPs": flops_pass / t_adj / 1e12,
+                             "GBps": bytes_pass / t_adj / 1e9}}
+        dom = "gemm_adj" if t_adj >= t_fwd else "gemm_fwd"
+        achieved, peak, unit, bound = kern[dom]["TFLOPs"], FP64_PEAK_TFLOPS, "TFLOP/s", "tensor"
+        peak_src = FP64_PEAK_SRC
+    else:
+        xv = eng.vec(x0)
+        t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemv_fwd(eng.plan, _lib.ptr(eng.Aw), _lib.ptr(xv),
+                                                               _lib.ptr(eng.d), s)), reps)
+        t_adj = time_kernel(lambda: _lib.check(lib.gi_gemv_adj(eng.plan, _lib.ptr(eng.Aw),
+                                                               _lib.ptr(eng.r), _lib.ptr(eng.g), s)), reps)
+        kern = {"gemv_fwd": {"ms": t_fwd * 1e3, "GBps": bytes_pass / t_fwd / 1e9},
+                "gemv_adj": {"ms": t_adj * 1e3, "GBps": bytes_pass / t_adj / 1e9}}
+        dom = "gemv_adj" if t_adj >= t_fwd else "gemv_fwd"
+        achieved, peak, unit, bound, peak_src = kern[dom]["GBps"], hbm_peak, "GB/s", "hbm", hbm_src
     if world > 1:
         t = torch.tensor([achieved], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
@@ -348,7 +403,25 @@ def gpu_arm(args):
 
     # ---- e2e: the public per-proposal call with host buffers (momentum in, state out) ----
     e2e = None
-    if world == 1:
+    if world == 1 and nch > 1:
+        # public batched call: per proposal the host draws L, p0 (randn) and u for every chain in the
+        # reference's RNG order, p0 goes host->device, accepted states come back device->host
+        done, nprop = 0, 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while done < args.steps:
+            out = bt.propose()
+            done += int(np.mean([o[1] for o in out]))
+            nprop += 1
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        steps_done = sum(L for c in range(nch) for (L, _) in bt.proposals[c])
+        e2e = {"value": steps_done / t_e2e, "unit": "leapfrog steps/s",
+               "h2d_bytes_per_step": int(nprop * nch * (8 * M + 12) / steps_done),
+               "d2h_bytes_per_step": int(nprop * nch * (8 * M + 80) / steps_done),
+               "proposals": nprop * nch, "api": "HMCBatch.propose -> gi_hmcb_propose (host RNG, "
+               "per-chain L in [5,20]; chains with short trajectories idle until the longest ends)"}
+    elif world == 1:
         np.random.seed(HMC["seed"])
         x = x0
         done, nprop = 0, 0
@@ -404,18 +477,18 @@ def gpu_arm(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, FP64 Aw "
-                                   "%.1f GB row-sharded over %d GPU(s), Damping, 1 chain; inputs "
+                                   "%.1f GB row-sharded over %d GPU(s), Damping, %d chain(s) batched as columns; inputs "
                                    "(%.1f GB per GPU per pass) exceed the 126 MB L2, no flush needed"
-                                   % (args.workload, nz, ny, nx, M, N, 8e-9 * N * M, world,
+                                   % (args.workload, nz, ny, nx, M, N, 8e-9 * N * M, world, nch,
                                       8e-9 * n_local * M),
-                       "voxels": M, "observations": N, "chains": 1, "parallelism": "rows%d" % world},
-            "gemv_hbm_GBps": (2 * bytes_pass * world) * steps_per_s / 1e9,
+                       "voxels": M, "observations": N, "chains": nch, "parallelism": "rows%d" % world},
+            "batch_steps_per_s": steps_per_s / nch,
+            "gemv_hbm_GBps": (2 * bytes_pass * world) * steps_per_s / nch / 1e9,
             "assembly": {"mpairs_per_s": N * M / t_asm / 1e6, "seconds": t_asm,
                          "weighting_seconds": t_wgt},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "kernels": kern,
-                         "frac_of_nominal_8TBps": achieved / 8000.0},
+            "roofline": {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak,
+                         "unit": unit, "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernels": kern, "hbm_peak_GBps": hbm_peak},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
         if cpu is not None:
@@ -460,6 +533,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=64,
+                    help="chains batched as columns (BASELINE.json configs[4]: 64); 1 = GEMV path")
     ap.add_argument("--cpu-rows", type=int, default=128, help="observation rows of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8, help="leapfrog steps per CPU chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -75,6 +75,25 @@ SIGNATURES = {
     "gi_hmc_leapfrog_steps": (C.c_int, [_P, _P, C.c_int32, _D]),
     "gi_hmc_launch_count": (_I64, [_P]),
     "gi_hmc_stream": (_P, [_P]),
+    "gi_plan_batch_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(_I64)]),
+    "gi_gemm_fwd": (C.c_int, [_P, _P, _P, _P, _P]),
+    "gi_data_sum_batched": (C.c_int, [_P, _P, _P, _P, _P]),
+    "gi_residual_batched": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P]),
+    "gi_gemm_adj": (C.c_int, [_P, _P, _P, _P, _P]),
+    "gi_update_batched": (C.c_int, [_P, C.POINTER(RegParams), _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _D, _P, C.c_int32, C.c_int32, _P, _P]),
+    "gi_hmcb_create": (C.c_int, [C.POINTER(HmcConfig), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P,
+                                 C.POINTER(_P)]),
+    "gi_hmcb_destroy": (C.c_int, [_P]),
+    "gi_hmcb_set_reg": (C.c_int, [_P, C.POINTER(RegParams)]),
+    "gi_hmcb_set_state": (C.c_int, [_P, _P]),
+    "gi_hmcb_get_state": (C.c_int, [_P, _P, _P, _P]),
+    "gi_hmcb_get_misfit": (C.c_int, [_P, _P, _P, _P, _P]),
+    "gi_hmcb_propose": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P]),
+    "gi_hmcb_propose_philox": (C.c_int, [_P, C.c_uint64, C.c_uint64, _D, _P, _D, _P]),
+    "gi_hmcb_leapfrog_steps": (C.c_int, [_P, _P, C.c_int32, _D]),
+    "gi_hmcb_launch_count": (_I64, [_P]),
+    "gi_hmcb_padded_chains": (C.c_int32, [_P]),
     "gi_dwt_db4_l2_1d": (C.c_int, [_P, _I64, _P, C.POINTER(_I64), _P]),
     "gi_dwt_db4_l2_3d": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int32 * 3), _P]),

@@ -1,0 +1,971 @@
+// batched.cu -- C independent chains batched as columns: the two big passes become dense FP64
+// contractions on the tensor cores (DMMA m8n8k4), streaming the kernel matrix once per pass for
+// ALL chains.
+//
+//   forward   D[c][l]  = sum_k Aw[l][k] * X[c][k]        (gemm_fwd_kernel)
+//   adjoint   Gt[c][k] = sum_l Aw[l][k] * R[c][l]        (gemm_adj_kernel)
+//
+// Replaces, for a batch of chains, the same reference lines as leapfrog.cu
+// (inversion/potential.py:688-717 data_all, :812-845 misfit_and_grad; inversion/hmc.py:85-177
+// _leapfrog); the reference runs one OS process per chain (example/*/run_main.sh:18
+// `mpiexec -n 2`), each streaming its own copy of Aw.
+//
+// Layouts: every per-chain vector is chain-major -- X, P, grad: [C][ld]; D: [C][nrows];
+// R: [C][npad] (npad = nrows rounded up to 16, padding zero).  C is padded to 8*NT, NT in {1,2,4,8}.
+//
+// Tiling (B200: 148 SMs, 227 KB smem/CTA, FP64 pipe 37.1 TFLOP/s measured for DFMA and DMMA alike,
+// profiles/r01_fp64_peak_probe.txt -- at C = 64 both passes are FP64-pipe bound, 16 flop/B):
+//   fwd: CTA = 128 rows x one k-chunk, 8 warps x (16 rows x 8*NT chains); 4-stage cp.async ring of
+//        [128 rows x 32 voxels] of Aw + [C x 32] of X per stage, XOR-swizzled 16-B chunks so every
+//        fragment read is a conflict-free LDS.128; consecutive CTAs share the k-chunk, so X is read
+//        from HBM once and served from L2 afterwards; partial[kc][c][row] summed in fixed order.
+//   adj: CTA = 256-voxel strip x ALL rows (no split, no partials), 8 warps x (32 voxels x 8*NT
+//        chains); 4-stage ring of [16 rows x 256 voxels] of Aw + [C x 16] of R.
+// The MMA k-slot <-> memory index assignment is permuted (a sum is order-free as long as A and B
+// agree) so that each thread's fragment elements are adjacent in shared memory.
+// Deterministic: fixed tile -> slot mapping, no floating-point atomics.
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "plan.cuh"
+
+namespace gi {
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void lds128(const void *smem, double &a, double &b) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(s));
+}
+__device__ __forceinline__ double lds64(const void *smem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    double a;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(s));
+    return a;
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); lane = 4*g + t holds A[g][t], B[t][g], C[g][2t], C[g][2t+1]
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int kGemmThreads = 256;
+constexpr int kStages = 4;
+constexpr int kFwdRows = 128;  // rows per CTA
+constexpr int kFwdK = 32;      // voxels per stage
+constexpr int kAdjCols = 256;  // voxels per CTA
+constexpr int kAdjK = 16;      // rows per stage
+
+template <int NT>
+__host__ __device__ constexpr int fwd_stage_bytes() { return kFwdRows * kFwdK * 8 + 8 * NT * kFwdK * 8; }
+template <int NT>
+__host__ __device__ constexpr int adj_stage_bytes() { return kAdjK * kAdjCols * 8 + 8 * NT * kAdjK * 8; }
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ X, int64_t nrows,
+                int64_t kchunk, int64_t rowblocks, double *__restrict__ part) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int C = 8 * NT;
+    constexpr int GB = kFwdRows * kFwdK * 8;
+    constexpr int STAGE = fwd_stage_bytes<NT>();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t tile = blockIdx.x;
+    const int64_t kc = tile / rowblocks, rb = tile - kc * rowblocks;
+    const int64_t r0 = rb * kFwdRows;
+    const int64_t c0 = kc * kchunk, c1 = min(c0 + kchunk, ld);
+    const int ntiles = (int)((c1 - c0) / kFwdK);
+
+    // this thread's copy slots: Aw rows (tid>>4) + 16u, 16-B chunk tid&15 (swizzled by row parity)
+    const int lrow = tid >> 4, lch = tid & 15;
+    const double *gsrc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        gsrc[u] = G + min(r0 + lrow + 16 * u, nrows - 1) * ld + c0 + 2 * lch;
+    const int gdst = lrow * 256 + ((lch ^ ((lrow & 1) << 2)) << 4);  // + 16u rows: parity unchanged
+
+    auto load_stage = [&](int s, int kt) {
+        unsigned char *base = smem + s * STAGE;
+        const int64_t koff = (int64_t)kt * kFwdK;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cp_async16(base + gdst + u * 16 * 256, gsrc[u] + koff);
+#pragma unroll
+        for (int u = 0; u < (C * 16 + kGemmThreads - 1) / kGemmThreads; ++u) {
+            const int id = tid + kGemmThreads * u;
+            if (C * 16 % kGemmThreads == 0 || id < C * 16) {
+                const int row = id >> 4;
+                cp_async16(base + GB + row * 256 + ((lch ^ ((row & 1) << 2)) << 4),
+                           X + (int64_t)row * ld + c0 + koff + 2 * lch);
+            }
+        }
+    };
+
+    double acc[2][NT][2];
+#pragma unroll
+    for (int rm = 0; rm < 2; ++rm)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[rm][j][0] = acc[rm][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if (s < ntiles) load_stage(s, s);
+        cp_async_commit();
+    }
+    const int sw = (g & 1) << 2;  // rows 16w + 8rm + g and chains 8j + g have the parity of g
+    for (int kt = 0; kt < ntiles; ++kt) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        if (kt + kStages - 1 < ntiles) load_stage((kt + kStages - 1) % kStages, kt + kStages - 1);
+        cp_async_commit();
+        const unsigned char *gs = smem + (kt % kStages) * STAGE;
+        const unsigned char *xs = gs + GB;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int ch_lo = ((8 * q + t) ^ sw) << 4, ch_hi = ((8 * q + 4 + t) ^ sw) << 4;
+            double a[2][4];
+#pragma unroll
+            for (int rm = 0; rm < 2; ++rm) {
+                const unsigned char *rowp = gs + (warp * 16 + rm * 8 + g) * 256;
+                lds128(rowp + ch_lo, a[rm][0], a[rm][1]);
+                lds128(rowp + ch_hi, a[rm][2], a[rm][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const unsigned char *rowp = xs + (8 * j + g) * 256;
+                double b[4];
+                lds128(rowp + ch_lo, b[0], b[1]);
+                lds128(rowp + ch_hi, b[2], b[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dmma884(acc[0][j][0], acc[0][j][1], a[0][i], b[i]);
+                    dmma884(acc[1][j][0], acc[1][j][1], a[1][i], b[i]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int rm = 0; rm < 2; ++rm) {
+        const int64_t row = r0 + warp * 16 + rm * 8 + g;
+        if (row < nrows) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int64_t chain = 8 * j + 2 * t;
+                part[(kc * C + chain) * nrows + row] = acc[rm][j][0];
+                part[(kc * C + chain + 1) * nrows + row] = acc[rm][j][1];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// adjoint
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ R, int64_t npad,
+                int64_t nrows, double *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int C = 8 * NT;
+    constexpr int GB = kAdjK * kAdjCols * 8;
+    constexpr int STAGE = adj_stage_bytes<NT>();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int64_t v0 = (int64_t)blockIdx.x * kAdjCols;
+    const int ntiles = (int)(npad / kAdjK);
+
+    // copy slots: Aw rows (tid>>7) + 2u of the stage, 16-B chunk tid&127 of the 256-voxel strip
+    const int lrow = tid >> 7, lcv = tid & 127;
+    const int64_t col = (v0 + 2 * lcv < ld) ? v0 + 2 * lcv : 0;  // strip tail: any valid address
+    const int rchain = tid >> 3, rec = tid & 7;
+
+    auto load_stage = [&](int s, int ot) {
+        unsigned char *base = smem + s * STAGE;
+        const int64_t o0 = (int64_t)ot * kAdjK;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int row = lrow + 2 * u;
+            cp_async16(base + row * 2048 + ((lcv ^ (2 * (row & 3))) << 4),
+                       G + min(o0 + row, nrows - 1) * ld + col);
+        }
+#pragma unroll
+        for (int u = 0; u < (C * 8 + kGemmThreads - 1) / kGemmThreads; ++u) {
+            const int chain = rchain + 32 * u;
+            if (C * 8 % kGemmThreads == 0 || chain < C)
+                cp_async16(base + GB + chain * 128 + ((rec ^ (2 * (chain & 3))) << 4),
+                           R + (int64_t)chain * npad + o0 + 2 * rec);
+        }
+    };
+
+    double acc[4][NT][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) {
+        if (s < ntiles) load_stage(s, s);
+        cp_async_commit();
+    }
+    const int a_lo = ((16 * warp + g) ^ (2 * t)) << 4, a_hi = ((16 * warp + 8 + g) ^ (2 * t)) << 4;
+    for (int ot = 0; ot < ntiles; ++ot) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();
+        if (ot + kStages - 1 < ntiles) load_stage((ot + kStages - 1) % kStages, ot + kStages - 1);
+        cp_async_commit();
+        const unsigned char *gs = smem + (ot % kStages) * STAGE;
+        const unsigned char *rs = gs + GB;
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+            const unsigned char *rowp = gs + (4 * kq + t) * 2048;
+            double a[4];
+            lds128(rowp + a_lo, a[0], a[1]);  // voxels 32w + 2g + {0,1}
+            lds128(rowp + a_hi, a[2], a[3]);  // voxels 32w + 16 + 2g + {0,1}
+            const int e = ((4 * kq + t) ^ (4 * (g & 3))) << 3;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double b = lds64(rs + (8 * j + g) * 128 + e);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
+            }
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int64_t v = v0 + 32 * warp + 16 * h + 2 * g;
+        if (v < ld) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e2 = 0; e2 < 2; ++e2) {
+                    double *dst = out + (int64_t)(8 * j + 2 * t + e2) * ld + v;
+                    asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst), "d"(acc[2 * h][j][e2]),
+                                 "d"(acc[2 * h + 1][j][e2])
+                                 : "memory");
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-chain data misfit (potential.py:699-706), one CTA per chain
+//  mode 0: d = sum_k part[k]; s0 = sum(d + fix); r = (d + fix - s0/n_total) - dobs_c; s1 = sum r^2
+//  mode 1: d = sum_k part[k]; s0 only         (row-sharded: s0 is all-reduced before mode 2)
+//  mode 2: r, s1 from d and sums[0]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+misfit_batched_kernel(int mode, const double *__restrict__ part, int64_t nkc, int64_t C, int64_t nrows,
+                      int64_t npad, int64_t n_total, double *__restrict__ d,
+                      const double *__restrict__ fix, const double *__restrict__ dobs_c,
+                      double *__restrict__ r, double *__restrict__ sums) {
+    __shared__ double scratch[32];
+    const int64_t chain = blockIdx.x;
+    double *dc = d + chain * nrows, *rc = r + chain * npad, *sc = sums + chain * 8;
+    double s0 = 0.0;
+    if (mode != 2) {
+        for (int64_t row = threadIdx.x; row < nrows; row += 1024) {
+            double tsum = 0.0;
+            for (int64_t k = 0; k < nkc; ++k) tsum += part[(k * C + chain) * nrows + row];
+            dc[row] = tsum;
+            s0 += fix ? tsum + fix[row] : tsum;
+        }
+        s0 = block_sum(s0, scratch);
+        if (threadIdx.x == 0) sc[0] = s0;
+        if (mode == 1) return;
+    } else {
+        s0 = sc[0];
+    }
+    const double mean = s0 / (double)n_total;
+    double s1 = 0.0;
+    for (int64_t row = threadIdx.x; row < npad; row += 1024) {
+        double rr = 0.0;
+        if (row < nrows) {
+            const double tv = dc[row];
+            const double dinv = fix ? tv + fix[row] : tv;
+            rr = (dinv - mean) - dobs_c[row];
+        }
+        rc[row] = rr;
+        s1 += rr * rr;
+    }
+    s1 = block_sum(s1, scratch);
+    if (threadIdx.x == 0) sc[1] = s1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched fused update: grid (ceil(M/256), C).  Per chain c and trajectory step `step`:
+//   step <  L[c]: p -= dt*grad, x += dt*p, clamp         (hmc.py:118-150)
+//   step == L[c]: p -= dt/2*grad, grad_out written       (hmc.py:152)
+//   step >  L[c]: frozen (the chain's trajectory is over; x copied, sums recomputed identically)
+//   step == 0   : the opening half step from the cached gradient (hmc.py:104-118)
+//   L[c] == 0   : inactive chain (frozen for the whole proposal)
+// ---------------------------------------------------------------------------------------------
+struct BatchCtl {
+    const int32_t *L;  // [C] or nullptr (uniform: every chain takes `uniform_mode`)
+    int32_t step;
+    int32_t uniform_mode;  // 0 full step, 1 final half step, 2 frozen, 3 opening half step
+    int64_t vec_stride;    // ld
+    int64_t nblocks;       // gridDim.x
+};
+
+__global__ void __launch_bounds__(kUpdThreads) update_batched_kernel(UpdateArgs a, BatchCtl ctl) {
+    const int64_t c = blockIdx.y;
+    int mode = ctl.uniform_mode;
+    if (ctl.L) {
+        const int32_t Lc = ctl.L[c];
+        if (Lc == 0) mode = 2;  // inactive chain: nothing moves
+        else if (ctl.step == 0) mode = 3;
+        else mode = (ctl.step < Lc) ? 0 : (ctl.step == Lc ? 1 : 2);
+    }
+    const int64_t off = c * ctl.vec_stride;
+    if (a.grad_in) a.grad_in += off;
+    if (a.gpart) a.gpart += off;
+    a.x_in += off;
+    a.mw_in += off;
+    a.p += off;
+    if (a.x_out) a.x_out += off;
+    if (a.mw_out) a.mw_out += off;
+    if (a.grad_out) a.grad_out += off;
+    a.blockpart += c * 3 * ctl.nblocks;
+    a.counter += c;
+    a.sums += c * 8;
+    const double dt = a.dt;
+    if (mode == 0) { a.pcoef = dt; a.advance = 1; a.grad_out = nullptr; }
+    else if (mode == 1) { a.pcoef = 0.5 * dt; a.advance = 0; }
+    else if (mode == 2) { a.pcoef = 0.0; a.advance = 0; a.grad_out = nullptr; }
+    else { a.pcoef = 0.5 * dt; a.advance = 1; a.grad_out = nullptr; a.save_k0 = 1; }
+    update_body(a, true);
+}
+
+__global__ void transform_batched_kernel(const double *__restrict__ x, const double *__restrict__ low,
+                                         const double *__restrict__ high, double log_factor, int64_t M,
+                                         int64_t ld, double *__restrict__ mw) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const int64_t o = (int64_t)blockIdx.y * ld + j;
+    const double ex = pow(2.718281828459045, log_factor * x[o]);
+    mw[o] = (low[j] + high[j] * ex) / (1.0 + ex);
+}
+
+// Metropolis per chain (hmc.py:156-173); K0 of the opening half step is parked in sums[5]
+__global__ void metropolis_batched_kernel(DevState *st, const double *__restrict__ sums, double alpha,
+                                          const int32_t *__restrict__ L, int C, int force_accept) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double *s = sums + 8 * c;
+    DevState *sc = st + c;
+    if (L && L[c] == 0 && !force_accept) {  // inactive chain: state untouched, nothing to commit
+        sc->res.accept = 0;
+        sc->res.L = 0;
+        return;
+    }
+    const double Ud = s[1], Um = s[2], Knew = s[3], K0 = force_accept ? 0.0 : s[5];
+    const double Unew = Ud + alpha * Um;
+    const double Hcur = K0 + sc->U, Hnew = Knew + Unew;
+    const bool acc = force_accept || (Hnew < Hcur) || (sc->u < exp(-(Hnew - Hcur)));
+    if (acc) { sc->U = Unew; sc->Ud = Ud; sc->Um = Um; }
+    sc->res.accept = acc ? 1 : 0;
+    sc->res.L = L ? L[c] : 0;
+    sc->res.U = sc->U; sc->res.U_data = sc->Ud; sc->res.U_model = sc->Um;
+    sc->res.Hcur = Hcur; sc->res.Hnew = Hnew;
+    sc->res.Unew = Unew; sc->res.Unew_data = Ud; sc->res.Unew_model = Um;
+}
+
+__global__ void commit_batched_kernel(const DevState *__restrict__ st, int64_t M, int64_t N, int64_t ld,
+                                      const double *__restrict__ x, const double *__restrict__ mw,
+                                      const double *__restrict__ gnew, const double *__restrict__ d,
+                                      double *__restrict__ x_cur, double *__restrict__ mw_cur,
+                                      double *__restrict__ g_cur, double *__restrict__ d_cur) {
+    const int64_t c = blockIdx.y;
+    if (!st[c].res.accept) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < M) {
+        const int64_t o = c * ld + j;
+        x_cur[o] = x[o];
+        g_cur[o] = gnew[o];
+        if (mw_cur != x_cur) mw_cur[o] = mw[o];
+    }
+    if (j < N) d_cur[c * N + j] = d[c * N + j];
+}
+
+// device draws for chain c: momentum from Philox key (seed + c), like the reference's seed + myrank
+__global__ void philox_normal_batched_kernel(uint64_t seed, uint64_t counter, double sigma, int64_t M,
+                                             int64_t ld, double *__restrict__ p, DevState *st) {
+    const int64_t c = blockIdx.y;
+    const uint64_t sd = seed + (uint64_t)c;
+    const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cw[4] = {(uint32_t)tt, (uint32_t)(tt >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
+    philox4x32_10(cw, (uint32_t)sd, (uint32_t)(sd >> 32));
+    const double u1 = u53(cw[0], cw[1]), u2 = u53(cw[2], cw[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, co;
+    sincospi(2.0 * u2, &s, &co);
+    const int64_t j = 2 * tt;
+    double *pc = p + c * ld;
+    if (j < M) pc[j] = rad * co * sigma;
+    if (j + 1 < M) pc[j + 1] = rad * s * sigma;
+    if (tt == 0) {
+        uint32_t c2[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)counter, (uint32_t)(counter >> 32)};
+        philox4x32_10(c2, (uint32_t)sd, (uint32_t)(sd >> 32));
+        st[c].u = u53(c2[0], c2[1]);
+    }
+}
+
+__global__ void set_u_kernel(DevState *st, const double *__restrict__ u, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) st[c].u = u[c];
+}
+
+}  // namespace gi
+
+using namespace gi;
+
+// =============================================================================================
+// batched plan pieces (declared in plan.cuh, used by gi_plan_* in leapfrog.cu)
+// =============================================================================================
+static int pick_nt(int nchains) { return nchains <= 8 ? 1 : nchains <= 16 ? 2 : nchains <= 32 ? 4 : 8; }
+
+template <int NT>
+static int set_smem_attrs() {
+    GI_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kStages * fwd_stage_bytes<NT>()));
+    GI_CUDA(cudaFuncSetAttribute(gemm_adj_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kStages * adj_stage_bytes<NT>()));
+    return GI_OK;
+}
+
+int gi::batched_plan_init(gi_plan *p) {
+    GI_REQUIRE(p->nchains >= 2 && p->nchains <= 64, "gi_plan_create: 1..64 chains per plan");
+    GI_REQUIRE(p->ld % 32 == 0, "gi_plan_create: batched plans need ld %% 32 == 0");
+    p->b_nt = pick_nt(p->nchains);
+    p->b_C = 8 * p->b_nt;
+    p->b_npad = ceil_div(p->nrows, kAdjK) * kAdjK;
+    p->b_rowblocks = ceil_div(p->nrows, kFwdRows);
+    // k-chunks: aim at ~32 waves of one CTA per SM; chunk a multiple of the 32-voxel stage
+    const int sms = sm_count();
+    int64_t nkc = std::max<int64_t>(1, (32LL * sms) / p->b_rowblocks);
+    nkc = std::min<int64_t>(nkc, ceil_div(p->ld, 8 * kFwdK));  // >= 8 stages per CTA
+    nkc = std::max<int64_t>(nkc, 1);
+    p->b_kchunk = ceil_div(ceil_div(p->ld, nkc), kFwdK) * kFwdK;
+    p->b_nkc = ceil_div(p->ld, p->b_kchunk);
+    p->b_strips = ceil_div(p->ld, kAdjCols);
+    const size_t b_part = sizeof(double) * p->b_nkc * p->b_C * p->nrows;
+    const size_t b_blk = sizeof(double) * 3 * p->upd_blocks * p->b_C;
+    cudaError_t e = cudaMalloc(&p->b_part, b_part);
+    if (e == cudaSuccess) e = cudaMalloc(&p->b_blockpart, b_blk);
+    if (e == cudaSuccess) e = cudaMalloc(&p->b_scratch_sums, sizeof(double) * 8 * p->b_C);
+    if (e == cudaSuccess) e = cudaMalloc(&p->b_counter, sizeof(unsigned int) * p->b_C);
+    if (e == cudaSuccess) e = cudaMemset(p->b_counter, 0, sizeof(unsigned int) * p->b_C);
+    if (e != cudaSuccess) return cuda_fail(e, "batched plan workspace", __FILE__, __LINE__);
+    p->workspace_bytes += (int64_t)(b_part + b_blk);
+    switch (p->b_nt) {
+        case 1: return set_smem_attrs<1>();
+        case 2: return set_smem_attrs<2>();
+        case 4: return set_smem_attrs<4>();
+        default: return set_smem_attrs<8>();
+    }
+}
+
+void gi::batched_plan_free(gi_plan *p) {
+    cudaFree(p->b_part);
+    cudaFree(p->b_blockpart);
+    cudaFree(p->b_scratch_sums);
+    cudaFree(p->b_counter);
+}
+
+int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s) {
+    const unsigned grid = (unsigned)(p->b_nkc * p->b_rowblocks);
+#define GI_FWD(NT)                                                                             \
+    gemm_fwd_kernel<NT><<<grid, kGemmThreads, kStages * fwd_stage_bytes<NT>(), s>>>(           \
+        G, p->ld, X, p->nrows, p->b_kchunk, p->b_rowblocks, p->b_part)
+    switch (p->b_nt) {
+        case 1: GI_FWD(1); break;
+        case 2: GI_FWD(2); break;
+        case 4: GI_FWD(4); break;
+        default: GI_FWD(8); break;
+    }
+#undef GI_FWD
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s) {
+    const unsigned grid = (unsigned)p->b_strips;
+#define GI_ADJ(NT)                                                                             \
+    gemm_adj_kernel<NT><<<grid, kGemmThreads, kStages * adj_stage_bytes<NT>(), s>>>(           \
+        G, p->ld, R, p->b_npad, p->nrows, out)
+    switch (p->b_nt) {
+        case 1: GI_ADJ(1); break;
+        case 2: GI_ADJ(2); break;
+        case 4: GI_ADJ(4); break;
+        default: GI_ADJ(8); break;
+    }
+#undef GI_ADJ
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+int gi::launch_misfit_batched(gi_plan *p, int mode, int64_t n_total, double *d, const double *fix,
+                              const double *dobs_c, double *r, double *sums, cudaStream_t s) {
+    misfit_batched_kernel<<<(unsigned)p->b_C, 1024, 0, s>>>(mode, p->b_part, p->b_nkc, p->b_C, p->nrows,
+                                                            p->b_npad, n_total, d, fix, dobs_c, r, sums);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+int gi::launch_update_batched(gi_plan *p, const gi_reg_params *reg, const double *grad_in,
+                              const double *gdata, const double *x_in, const double *mw_in,
+                              const double *mwapr, const double *wmsq, const double *low,
+                              const double *high, double *pm, double *x_out, double *mw_out,
+                              double *grad_out, double dt, const int32_t *L_dev, int step,
+                              int uniform_mode, double *sums, cudaStream_t s) {
+    UpdateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.grad_in = grad_in; a.gpart = gdata; a.gparts = 1;
+    a.x_in = x_in; a.mw_in = mw_in; a.mwapr = mwapr; a.wmsq = wmsq; a.low = low; a.high = high;
+    a.p = pm; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;
+    a.dt = dt; a.M = p->M; a.ld = p->ld; a.reg = *reg;
+    a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = sums;
+    BatchCtl ctl;
+    ctl.L = L_dev; ctl.step = step; ctl.uniform_mode = uniform_mode; ctl.vec_stride = p->ld;
+    ctl.nblocks = p->upd_blocks;
+    dim3 grid((unsigned)p->upd_blocks, (unsigned)p->b_C);
+    update_batched_kernel<<<grid, kUpdThreads, 0, s>>>(a, ctl);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+// =============================================================================================
+// building blocks for C chains (row-sharded driver) -- same roles as gi_gemv_fwd & co.
+// =============================================================================================
+extern "C" int gi_plan_batch_info(const gi_plan *p, int32_t *padded_chains, int64_t *padded_rows) {
+    GI_REQUIRE(p && p->nchains > 1, "gi_plan_batch_info: not a batched plan");
+    if (padded_chains) *padded_chains = (int32_t)p->b_C;
+    if (padded_rows) *padded_rows = p->b_npad;
+    return GI_OK;
+}
+
+extern "C" int gi_gemm_fwd(gi_plan *p, const double *G, const double *X, double *D, void *stream) {
+    GI_REQUIRE(p && G && X && D, "gi_gemm_fwd: null pointer");
+    GI_REQUIRE(p->nchains > 1, "gi_gemm_fwd: plan was created for one chain (use gi_gemv_fwd)");
+    int rc = launch_gemm_fwd(p, G, X, (cudaStream_t)stream);
+    if (rc) return rc;
+    // mode 1 with a scratch sums row would also do; D = sum of partials is all that is needed here
+    return launch_misfit_batched(p, 1, p->nrows, D, nullptr, nullptr, nullptr, p->b_scratch_sums,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int gi_data_sum_batched(gi_plan *p, const double *D, const double *fix, double *sums,
+                                   void *stream) {
+    GI_REQUIRE(p && D && sums && p->nchains > 1, "gi_data_sum_batched: bad argument");
+    // s0[c] = sum_l (D[c][l] + fix[l]) -- reuse mode 1 on a single "partial" (D itself)
+    misfit_batched_kernel<<<(unsigned)p->b_C, 1024, 0, (cudaStream_t)stream>>>(
+        1, D, 1, p->b_C, p->nrows, p->b_npad, p->nrows, const_cast<double *>(D), fix, nullptr, nullptr,
+        sums);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_residual_batched(gi_plan *p, const double *D, const double *fix,
+                                   const double *dobs_c, int64_t n_total, double *R, double *sums,
+                                   void *stream) {
+    GI_REQUIRE(p && D && dobs_c && R && sums && n_total > 0 && p->nchains > 1,
+               "gi_residual_batched: bad argument");
+    return launch_misfit_batched(p, 2, n_total, const_cast<double *>(D), fix, dobs_c, R, sums,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int gi_gemm_adj(gi_plan *p, const double *G, const double *R, double *Gt, void *stream) {
+    GI_REQUIRE(p && G && R && Gt && p->nchains > 1, "gi_gemm_adj: bad argument");
+    return launch_gemm_adj(p, G, R, Gt, (cudaStream_t)stream);
+}
+
+extern "C" int gi_update_batched(gi_plan *p, const gi_reg_params *reg, const double *grad_in_dev,
+                                 const double *gdata_dev, const double *x_in, const double *mw_in,
+                                 const double *mwapr, const double *wmsq, const double *low,
+                                 const double *high, double *pm, double *x_out, double *mw_out,
+                                 double *grad_out, double dt, const int32_t *L_dev, int32_t step,
+                                 int32_t uniform_mode, double *sums, void *stream) {
+    GI_REQUIRE(p && (gdata_dev || grad_in_dev) && x_in && mw_in && mwapr && pm && sums && x_out &&
+                   mw_out && low && high && p->nchains > 1,
+               "gi_update_batched: bad argument");
+    GI_REQUIRE(x_out != x_in, "gi_update_batched: x_in and x_out may not alias");
+    GI_REQUIRE(uniform_mode >= 0 && uniform_mode <= 3, "gi_update_batched: bad mode");
+    int rc = check_reg(reg, p->M);
+    if (rc) return rc;
+    GI_REQUIRE(reg->reg_kind != GI_REG_MS || wmsq, "gi_update_batched: MS needs wmsq");
+    return launch_update_batched(p, reg, grad_in_dev, gdata_dev, x_in, mw_in, mwapr, wmsq, low, high,
+                                 pm, x_out, mw_out, grad_out, dt, L_dev, step, uniform_mode, sums,
+                                 (cudaStream_t)stream);
+}
+
+// =============================================================================================
+// single-GPU device-resident batched sampler
+// =============================================================================================
+struct gi_hmcb {
+    gi_hmc_config cfg;
+    int32_t nchains, C;  // user chains, padded chains
+    gi_plan *plan;
+    const double *G;
+    cudaStream_t stream;
+    double *x_cur, *mw_cur, *g_cur, *xa, *xb, *mwa, *mwb, *p, *gnew, *gdata;  // [C][ld]
+    double *low, *high, *mwapr, *wmsq;                                          // [ld]
+    double *d_cur, *d, *r, *dobs_c, *fix;  // [C][N], [C][N], [C][npad], [N], [N]
+    double *sums, *u_dev;                  // [C][8], [C]
+    int32_t *L_dev;
+    DevState *st, *st_host;
+    bool has_state;
+    int64_t launches;
+};
+
+static void hmcb_free(gi_hmcb *h) {
+    if (!h) return;
+    const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
+    double *bufs[] = {h->x_cur, h->g_cur, h->xa, h->xb, h->p, h->gnew, h->gdata, h->low, h->high,
+                      h->mwapr, h->wmsq, h->d_cur, h->d, h->r, h->dobs_c, h->fix, h->sums, h->u_dev};
+    for (double *b : bufs) cudaFree(b);
+    if (logc) { cudaFree(h->mw_cur); cudaFree(h->mwa); cudaFree(h->mwb); }
+    cudaFree(h->L_dev);
+    cudaFree(h->st);
+    if (h->st_host) cudaFreeHost(h->st_host);
+    gi_plan_destroy(h->plan);
+    delete h;
+}
+
+#define HB_CUDA(h, call)                                             \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) {                                    \
+            hmcb_free(h);                                            \
+            return gi::cuda_fail(e__, #call, __FILE__, __LINE__);    \
+        }                                                            \
+    } while (0)
+
+extern "C" int gi_hmcb_create(const gi_hmc_config *cfg, int32_t nchains, const double *G,
+                              const double *dobs_host, const double *gravfix_host,
+                              const double *low_host, const double *high_host,
+                              const double *mwapr_host, const double *wmsq_host, void *stream,
+                              gi_hmcb **out) {
+    GI_REQUIRE(cfg && G && dobs_host && low_host && high_host && mwapr_host && out,
+               "gi_hmcb_create: null pointer");
+    GI_REQUIRE(cfg->N > 0 && cfg->M > 0 && cfg->ld >= cfg->M && cfg->ld % 32 == 0,
+               "gi_hmcb_create: bad shape (ld must be a multiple of 32)");
+    GI_REQUIRE(nchains >= 2 && nchains <= 64, "gi_hmcb_create: 2..64 chains per batch");
+    int rc = check_reg(&cfg->reg, cfg->M);
+    if (rc) return rc;
+    GI_REQUIRE(!cfg->fixed || gravfix_host, "gi_hmcb_create: fixed=True needs grav_fix");
+    gi_hmcb *h = new gi_hmcb();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->G = G;
+    h->nchains = nchains;
+    h->stream = (cudaStream_t)stream;
+    rc = gi_plan_create(cfg->N, cfg->M, cfg->ld, nchains, &h->plan);
+    if (rc) { delete h; return rc; }
+    const int64_t C = h->C = h->plan->b_C, ld = cfg->ld, N = cfg->N, npad = h->plan->b_npad;
+    const bool logc = cfg->reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
+    const size_t bm = sizeof(double) * ld, bcm = bm * C, bn = sizeof(double) * N;
+    double **cmv[] = {&h->x_cur, &h->g_cur, &h->xa, &h->xb, &h->p, &h->gnew, &h->gdata};
+    for (double **b : cmv) {
+        HB_CUDA(h, cudaMalloc(b, bcm));
+        HB_CUDA(h, cudaMemsetAsync(*b, 0, bcm, h->stream));
+    }
+    if (logc) {
+        double **lv[] = {&h->mw_cur, &h->mwa, &h->mwb};
+        for (double **b : lv) {
+            HB_CUDA(h, cudaMalloc(b, bcm));
+            HB_CUDA(h, cudaMemsetAsync(*b, 0, bcm, h->stream));
+        }
+    } else {
+        h->mw_cur = h->x_cur; h->mwa = h->xa; h->mwb = h->xb;
+    }
+    double **mv[] = {&h->low, &h->high, &h->mwapr, &h->wmsq};
+    for (double **b : mv) {
+        HB_CUDA(h, cudaMalloc(b, bm));
+        HB_CUDA(h, cudaMemsetAsync(*b, 0, bm, h->stream));
+    }
+    HB_CUDA(h, cudaMalloc(&h->d_cur, bn * C));
+    HB_CUDA(h, cudaMalloc(&h->d, bn * C));
+    HB_CUDA(h, cudaMalloc(&h->r, sizeof(double) * npad * C));
+    HB_CUDA(h, cudaMalloc(&h->dobs_c, bn));
+    HB_CUDA(h, cudaMalloc(&h->fix, bn));
+    HB_CUDA(h, cudaMemsetAsync(h->d_cur, 0, bn * C, h->stream));
+    HB_CUDA(h, cudaMemsetAsync(h->d, 0, bn * C, h->stream));
+    HB_CUDA(h, cudaMemsetAsync(h->r, 0, sizeof(double) * npad * C, h->stream));
+    HB_CUDA(h, cudaMemsetAsync(h->fix, 0, bn, h->stream));
+    HB_CUDA(h, cudaMalloc(&h->sums, sizeof(double) * 8 * C));
+    HB_CUDA(h, cudaMemsetAsync(h->sums, 0, sizeof(double) * 8 * C, h->stream));
+    HB_CUDA(h, cudaMalloc(&h->u_dev, sizeof(double) * C));
+    HB_CUDA(h, cudaMalloc(&h->L_dev, sizeof(int32_t) * C));
+    HB_CUDA(h, cudaMemsetAsync(h->L_dev, 0, sizeof(int32_t) * C, h->stream));
+    HB_CUDA(h, cudaMalloc(&h->st, sizeof(DevState) * C));
+    HB_CUDA(h, cudaMemsetAsync(h->st, 0, sizeof(DevState) * C, h->stream));
+    HB_CUDA(h, cudaMallocHost(&h->st_host, sizeof(DevState) * C));
+    const size_t vm = sizeof(double) * cfg->M;
+    HB_CUDA(h, cudaMemcpyAsync(h->low, low_host, vm, cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(h->high, high_host, vm, cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaMemcpyAsync(h->mwapr, mwapr_host, vm, cudaMemcpyHostToDevice, h->stream));
+    if (wmsq_host)
+        HB_CUDA(h, cudaMemcpyAsync(h->wmsq, wmsq_host, vm, cudaMemcpyHostToDevice, h->stream));
+    {
+        double *tmp = new double[N];
+        long double acc = 0.0L;
+        for (int64_t i = 0; i < N; ++i) acc += dobs_host[i];
+        const double mean = (double)(acc / (long double)N);
+        for (int64_t i = 0; i < N; ++i) tmp[i] = dobs_host[i] - mean;
+        cudaError_t e = cudaMemcpyAsync(h->dobs_c, tmp, bn, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        delete[] tmp;
+        HB_CUDA(h, e);
+    }
+    if (cfg->fixed)
+        HB_CUDA(h, cudaMemcpyAsync(h->fix, gravfix_host, bn, cudaMemcpyHostToDevice, h->stream));
+    HB_CUDA(h, cudaStreamSynchronize(h->stream));
+    *out = h;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_destroy(gi_hmcb *h) {
+    if (h) cudaStreamSynchronize(h->stream);
+    hmcb_free(h);
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_set_reg(gi_hmcb *h, const gi_reg_params *reg) {
+    GI_REQUIRE(h && reg, "gi_hmcb_set_reg: null pointer");
+    int rc = check_reg(reg, h->cfg.M);
+    if (rc) return rc;
+    GI_REQUIRE(reg->constraint == h->cfg.reg.constraint,
+               "gi_hmcb_set_reg: the constraint is fixed at creation");
+    h->cfg.reg = *reg;
+    h->has_state = false;
+    return GI_OK;
+}
+
+// one batched misfit_and_grad at (x_in, mw_in) + the fused update
+static int hb_grad_eval_and_update(gi_hmcb *h, const double *x_in, const double *mw_in, double *x_out,
+                                   double *mw_out, double *grad_out, double dt, const int32_t *L_dev,
+                                   int step, int uniform_mode) {
+    gi_plan *p = h->plan;
+    cudaStream_t s = h->stream;
+    int rc = launch_gemm_fwd(p, h->G, mw_in, s);
+    if (rc) return rc;
+    rc = launch_misfit_batched(p, 0, p->nrows, h->d, h->cfg.fixed ? h->fix : nullptr, h->dobs_c, h->r,
+                               h->sums, s);
+    if (rc) return rc;
+    rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
+    if (rc) return rc;
+    rc = launch_update_batched(p, &h->cfg.reg, nullptr, h->gdata, x_in, mw_in, h->mwapr, h->wmsq,
+                               h->low, h->high, h->p, x_out, mw_out, grad_out, dt, L_dev, step,
+                               uniform_mode, h->sums, s);
+    h->launches += 4;
+    return rc;
+}
+
+extern "C" int gi_hmcb_set_state(gi_hmcb *h, const double *x_host) {
+    GI_REQUIRE(h && x_host, "gi_hmcb_set_state: null pointer");
+    cudaStream_t s = h->stream;
+    const int64_t M = h->cfg.M, ld = h->cfg.ld, C = h->C;
+    GI_CUDA(cudaMemsetAsync(h->x_cur, 0, sizeof(double) * ld * C, s));
+    GI_CUDA(cudaMemcpy2DAsync(h->x_cur, sizeof(double) * ld, x_host, sizeof(double) * M,
+                              sizeof(double) * M, h->nchains, cudaMemcpyHostToDevice, s));
+    if (h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC) {
+        dim3 grid((unsigned)ceil_div(M, 256), (unsigned)C);
+        transform_batched_kernel<<<grid, 256, 0, s>>>(h->x_cur, h->low, h->high, h->cfg.reg.log_factor,
+                                                      M, ld, h->mw_cur);
+        GI_LAUNCH_CHECK();
+        h->launches += 1;
+    }
+    GI_CUDA(cudaMemsetAsync(h->p, 0, sizeof(double) * ld * C, s));
+    // gradient at the start state: "final half step" mode with p = 0 writes grad_out = g_cur;
+    // x_out is a scratch copy
+    int rc = hb_grad_eval_and_update(h, h->x_cur, h->mw_cur, h->xa, h->mwa, h->g_cur, 0.0, nullptr, 0, 1);
+    if (rc) return rc;
+    metropolis_batched_kernel<<<1, 64, 0, s>>>(h->st, h->sums, h->cfg.reg.alpha, nullptr, (int)C, 1);
+    GI_LAUNCH_CHECK();
+    GI_CUDA(cudaMemcpyAsync(h->d_cur, h->d, sizeof(double) * h->cfg.N * C, cudaMemcpyDeviceToDevice, s));
+    h->launches += 1;
+    GI_CUDA(cudaStreamSynchronize(s));
+    h->has_state = true;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_get_state(gi_hmcb *h, double *x_host, double *d_host, double *mw_host) {
+    GI_REQUIRE(h && h->has_state, "gi_hmcb_get_state: no state set");
+    cudaStream_t s = h->stream;
+    const int64_t M = h->cfg.M, ld = h->cfg.ld, N = h->cfg.N;
+    if (x_host)
+        GI_CUDA(cudaMemcpy2DAsync(x_host, sizeof(double) * M, h->x_cur, sizeof(double) * ld,
+                                  sizeof(double) * M, h->nchains, cudaMemcpyDeviceToHost, s));
+    if (mw_host)
+        GI_CUDA(cudaMemcpy2DAsync(mw_host, sizeof(double) * M, h->mw_cur, sizeof(double) * ld,
+                                  sizeof(double) * M, h->nchains, cudaMemcpyDeviceToHost, s));
+    if (d_host)
+        GI_CUDA(cudaMemcpyAsync(d_host, h->d_cur, sizeof(double) * N * h->nchains,
+                                cudaMemcpyDeviceToHost, s));
+    GI_CUDA(cudaStreamSynchronize(s));
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_get_misfit(gi_hmcb *h, double *U, double *Ud, double *Um, double *grad_host) {
+    GI_REQUIRE(h && h->has_state, "gi_hmcb_get_misfit: no state set");
+    cudaStream_t s = h->stream;
+    GI_CUDA(cudaMemcpyAsync(h->st_host, h->st, sizeof(DevState) * h->C, cudaMemcpyDeviceToHost, s));
+    if (grad_host)
+        GI_CUDA(cudaMemcpy2DAsync(grad_host, sizeof(double) * h->cfg.M, h->g_cur,
+                                  sizeof(double) * h->cfg.ld, sizeof(double) * h->cfg.M, h->nchains,
+                                  cudaMemcpyDeviceToHost, s));
+    GI_CUDA(cudaStreamSynchronize(s));
+    for (int c = 0; c < h->nchains; ++c) {
+        if (U) U[c] = h->st_host[c].U;
+        if (Ud) Ud[c] = h->st_host[c].Ud;
+        if (Um) Um[c] = h->st_host[c].Um;
+    }
+    return GI_OK;
+}
+
+// trajectories of all chains from their current states; momenta already in h->p, L in h->L_dev
+static int hb_run(gi_hmcb *h, int32_t Lmax, double dt, const int32_t *L_dev, gi_hmc_result *results,
+                  double *trace_x_host, double *trace_U_host, bool metropolis) {
+    cudaStream_t s = h->stream;
+    gi_plan *p = h->plan;
+    const int64_t M = h->cfg.M, ld = h->cfg.ld, C = h->C, N = h->cfg.N;
+    const int nc = h->nchains;
+    const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
+    const double alpha = h->cfg.reg.alpha;
+    double *hs = nullptr;
+    if (trace_U_host) hs = new double[8 * C];
+    auto trace = [&](int i, const double *xbuf) -> int {
+        if (trace_x_host)
+            GI_CUDA(cudaMemcpy2DAsync(trace_x_host + (int64_t)i * nc * M, sizeof(double) * M, xbuf,
+                                      sizeof(double) * ld, sizeof(double) * M, nc,
+                                      cudaMemcpyDeviceToHost, s));
+        if (trace_U_host) {
+            if (i == 0) {
+                GI_CUDA(cudaMemcpyAsync(h->st_host, h->st, sizeof(DevState) * C, cudaMemcpyDeviceToHost, s));
+                GI_CUDA(cudaStreamSynchronize(s));
+                for (int c = 0; c < nc; ++c) trace_U_host[c] = h->st_host[c].U;
+            } else {
+                GI_CUDA(cudaMemcpyAsync(hs, h->sums, sizeof(double) * 8 * C, cudaMemcpyDeviceToHost, s));
+                GI_CUDA(cudaStreamSynchronize(s));
+                for (int c = 0; c < nc; ++c)
+                    trace_U_host[(int64_t)i * nc + c] = hs[8 * c + 1] + alpha * hs[8 * c + 2];
+            }
+        }
+        return GI_OK;
+    };
+    int rc = trace(0, h->x_cur);
+    // opening half step from the cached gradients (hmc.py:104-118); K0 -> sums[c][5]
+    if (!rc)
+        rc = launch_update_batched(p, &h->cfg.reg, h->g_cur, nullptr, h->x_cur, h->mw_cur, h->mwapr,
+                                   h->wmsq, h->low, h->high, h->p, h->xa, h->mwa, nullptr, dt, L_dev,
+                                   0, 3, h->sums, s);
+    h->launches += 1;
+    double *xin = h->xa, *xout = h->xb, *mwin = h->mwa, *mwout = h->mwb;
+    for (int i = 1; i <= Lmax && !rc; ++i) {
+        rc = hb_grad_eval_and_update(h, xin, mwin, xout, mwout, h->gnew, dt, L_dev, i,
+                                     metropolis ? 0 : 0);
+        if (!rc) rc = trace(i, xin);
+        double *tp = xin; xin = xout; xout = tp;
+        if (logc) { tp = mwin; mwin = mwout; mwout = tp; }
+        else { mwin = xin; mwout = xout; }
+    }
+    delete[] hs;
+    if (rc || !metropolis) return rc;
+    metropolis_batched_kernel<<<1, 64, 0, s>>>(h->st, h->sums, alpha, L_dev, (int)C, 0);
+    GI_LAUNCH_CHECK();
+    const int64_t n = std::max(M, N);
+    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)C);
+    commit_batched_kernel<<<grid, 256, 0, s>>>(h->st, M, N, ld, xin, mwin, h->gnew, h->d, h->x_cur,
+                                               h->mw_cur, h->g_cur, h->d_cur);
+    GI_LAUNCH_CHECK();
+    h->launches += 2;
+    GI_CUDA(cudaMemcpyAsync(h->st_host, h->st, sizeof(DevState) * C, cudaMemcpyDeviceToHost, s));
+    GI_CUDA(cudaStreamSynchronize(s));
+    if (results)
+        for (int c = 0; c < nc; ++c) results[c] = h->st_host[c].res;
+    return GI_OK;
+}
+
+static int hb_set_L(gi_hmcb *h, const int32_t *L_host, int32_t *Lmax) {
+    int32_t tmp[64];
+    *Lmax = 0;
+    for (int c = 0; c < h->C; ++c) {
+        tmp[c] = c < h->nchains ? L_host[c] : 0;
+        GI_REQUIRE(tmp[c] >= 0, "gi_hmcb_propose: L must be >= 0 (0 = chain sits this proposal out)");
+        *Lmax = std::max(*Lmax, tmp[c]);
+    }
+    GI_CUDA(cudaMemcpyAsync(h->L_dev, tmp, sizeof(int32_t) * h->C, cudaMemcpyHostToDevice, h->stream));
+    GI_CUDA(cudaStreamSynchronize(h->stream));  // tmp is a stack buffer
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_propose(gi_hmcb *h, const double *p0_host, const int32_t *L_host, double dt,
+                               const double *u_host, gi_hmc_result *results, double *trace_x_host,
+                               double *trace_U_host) {
+    GI_REQUIRE(h && p0_host && L_host && u_host && results, "gi_hmcb_propose: null pointer");
+    GI_REQUIRE(h->has_state, "gi_hmcb_propose: call gi_hmcb_set_state first");
+    cudaStream_t s = h->stream;
+    int32_t Lmax = 0;
+    int rc = hb_set_L(h, L_host, &Lmax);
+    if (rc) return rc;
+    GI_CUDA(cudaMemsetAsync(h->p, 0, sizeof(double) * h->cfg.ld * h->C, s));
+    GI_CUDA(cudaMemcpy2DAsync(h->p, sizeof(double) * h->cfg.ld, p0_host, sizeof(double) * h->cfg.M,
+                              sizeof(double) * h->cfg.M, h->nchains, cudaMemcpyHostToDevice, s));
+    GI_CUDA(cudaMemsetAsync(h->u_dev, 0, sizeof(double) * h->C, s));
+    GI_CUDA(cudaMemcpyAsync(h->u_dev, u_host, sizeof(double) * h->nchains, cudaMemcpyHostToDevice, s));
+    set_u_kernel<<<1, 64, 0, s>>>(h->st, h->u_dev, (int)h->C);
+    GI_LAUNCH_CHECK();
+    h->launches += 1;
+    return hb_run(h, Lmax, dt, h->L_dev, results, trace_x_host, trace_U_host, true);
+}
+
+extern "C" int gi_hmcb_propose_philox(gi_hmcb *h, uint64_t seed, uint64_t counter, double sigma,
+                                      const int32_t *L_host, double dt, gi_hmc_result *results) {
+    GI_REQUIRE(h && L_host && results, "gi_hmcb_propose_philox: null pointer");
+    GI_REQUIRE(h->has_state, "gi_hmcb_propose_philox: call gi_hmcb_set_state first");
+    int32_t Lmax = 0;
+    int rc = hb_set_L(h, L_host, &Lmax);
+    if (rc) return rc;
+    const int64_t pairs = ceil_div(h->cfg.M, 2);
+    dim3 grid((unsigned)ceil_div(pairs, 256), (unsigned)h->C);
+    philox_normal_batched_kernel<<<grid, 256, 0, h->stream>>>(seed, counter, sigma, h->cfg.M, h->cfg.ld,
+                                                             h->p, h->st);
+    GI_LAUNCH_CHECK();
+    h->launches += 1;
+    return hb_run(h, Lmax, dt, h->L_dev, results, nullptr, nullptr, true);
+}
+
+extern "C" int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t nsteps, double dt) {
+    GI_REQUIRE(h, "gi_hmcb_leapfrog_steps: null handle");
+    GI_REQUIRE(h->has_state, "gi_hmcb_leapfrog_steps: call gi_hmcb_set_state first");
+    GI_REQUIRE(nsteps >= 1, "gi_hmcb_leapfrog_steps: nsteps must be >= 1");
+    cudaStream_t s = h->stream;
+    if (p0_dev)
+        GI_CUDA(cudaMemcpyAsync(h->p, p0_dev, sizeof(double) * h->cfg.ld * h->C,
+                                cudaMemcpyDeviceToDevice, s));
+    else
+        GI_CUDA(cudaMemsetAsync(h->p, 0, sizeof(double) * h->cfg.ld * h->C, s));
+    // every chain takes nsteps full steps: L = nsteps + 1 is never reached
+    int32_t tmp[64];
+    for (int c = 0; c < 64; ++c) tmp[c] = nsteps + 1;
+    GI_CUDA(cudaMemcpyAsync(h->L_dev, tmp, sizeof(int32_t) * h->C, cudaMemcpyHostToDevice, s));
+    GI_CUDA(cudaStreamSynchronize(s));
+    return hb_run(h, nsteps, dt, h->L_dev, nullptr, nullptr, nullptr, false);
+}
+
+extern "C" int64_t gi_hmcb_launch_count(const gi_hmcb *h) { return h ? h->launches : 0; }
+extern "C" int32_t gi_hmcb_padded_chains(const gi_hmcb *h) { return h ? h->C : 0; }

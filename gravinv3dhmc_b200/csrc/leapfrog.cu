@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "plan.cuh"
 
 namespace gi {
 
@@ -214,155 +215,6 @@ __global__ void adj_reduce_kernel(const double *__restrict__ part, int64_t ld, i
     g[c] = t;
 }
 
-// ---------------------------------------------------------------------------------------------
-// fused M-vector pass: gradient assembly + regulariser + leapfrog update + clamp
-// ---------------------------------------------------------------------------------------------
-constexpr int kUpdThreads = 256;
-
-struct UpdateArgs {
-    // gradient source: either grad_in (full gradient, e.g. cached at the current state) or
-    // 2*sum_k gpart[k] + alpha*dR
-    const double *grad_in;
-    const double *gpart;
-    int64_t gparts;  // number of partial vectors (stride ld)
-    const double *x_in, *mw_in, *mwapr, *wmsq, *low, *high;
-    double *p, *x_out, *mw_out, *grad_out;
-    double pcoef, dt;
-    int advance;
-    int64_t M, ld;
-    gi_reg_params reg;
-    double *blockpart;      // [gridDim.x][3]
-    unsigned int *counter;  // last-block ticket
-    double *sums;           // [2] = Um, [3] = K after update, [4] = K before update
-};
-
-__device__ __forceinline__ double reg_delta(const UpdateArgs &a, int64_t j) {
-    return a.mw_in[j] - a.mwapr[j];
-}
-
-__global__ void __launch_bounds__(kUpdThreads) update_kernel(UpdateArgs a) {
-    __shared__ double scratch[32];
-    __shared__ bool is_last;
-    const int64_t j = (int64_t)blockIdx.x * kUpdThreads + threadIdx.x;
-    double um = 0.0, k_after = 0.0, k_before = 0.0;
-    if (j < a.M) {
-        double grad;
-        if (a.grad_in) {
-            grad = a.grad_in[j];
-        } else {
-            double gd = 0.0;
-            for (int64_t k = 0; k < a.gparts; ++k) gd += a.gpart[k * a.ld + j];
-            gd = 2.0 * gd;  // potential.py:708  2 * np.dot(Aw.T, r)
-            const double dl = reg_delta(a, j);
-            double gm = 0.0;
-            const double beta = a.reg.beta;
-            switch (a.reg.reg_kind) {
-                case GI_REG_DAMPING:  // potential.py:775-784
-                    um = dl * dl;
-                    gm = 2.0 * dl;
-                    break;
-                case GI_REG_MS: {  // potential.py:719-736
-                    const double sq = dl * dl, w = a.wmsq[j], den = sq + beta;
-                    um = (w * sq) / den;
-                    gm = ((2.0 * beta) * w * dl) / (den * den);
-                    break;
-                }
-                case GI_REG_SMOOTHNESS:  // potential.py:786-796, D = fd3d (forward differences)
-                case GI_REG_TV: {        // potential.py:798-810
-                    const int nx = a.reg.nx, ny = a.reg.ny, nz = a.reg.nz;
-                    const int64_t nxy = (int64_t)nx * ny;
-                    const int k = (int)(j / nxy);
-                    const int rem = (int)(j - (int64_t)k * nxy);
-                    const int jy = rem / nx, ix = rem - jy * nx;
-                    const bool tv = a.reg.reg_kind == GI_REG_TV;
-                    // forward neighbours: rows of D owned by this cell  t = dl - d_next
-                    // backward neighbours: rows of D owned by the previous cell  t = d_prev - dl
-                    const int64_t offs[3] = {1, nx, nxy};
-                    const bool has_f[3] = {ix + 1 < nx, jy + 1 < ny, k + 1 < nz};
-                    const bool has_b[3] = {ix > 0, jy > 0, k > 0};
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        if (has_f[d]) {
-                            const double t = dl - reg_delta(a, j + offs[d]);
-                            if (tv) {
-                                const double s = sqrt(t * t + beta);
-                                um += s;
-                                gm += t / s;
-                            } else {
-                                um += t * t;
-                                gm += 2.0 * t;
-                            }
-                        }
-                        if (has_b[d]) {
-                            const double t = reg_delta(a, j - offs[d]) - dl;
-                            if (tv) gm -= t / sqrt(t * t + beta);
-                            else gm -= 2.0 * t;
-                        }
-                    }
-                    break;
-                }
-                default: break;
-            }
-            grad = gd + a.reg.alpha * gm;  // potential.py:843
-        }
-        if (a.grad_out) a.grad_out[j] = grad;
-        double p = a.p[j];
-        k_before = p * p;
-        p = __dsub_rn(p, __dmul_rn(a.pcoef, grad));  // hmc.py:114,150,152
-        if (a.advance) {
-            double x = __dadd_rn(a.x_in[j], __dmul_rn(a.dt, p));  // hmc.py:118
-            double mw = x;
-            if (a.reg.constraint == GI_CONSTRAINT_MANDATORY) {
-                // hmc.py:135-141 clamp and flip (the while loop runs once)
-                const double hi = a.high[j], lo = a.low[j];
-                if (x > hi) { x = hi; p = -p; }
-                else if (x < lo) { x = lo; p = -p; }
-                mw = x;
-            } else {
-                // potential.py:819-820  mw = (low + high*e**(f x)) / (1 + e**(f x))
-                const double ex = pow(2.718281828459045, a.reg.log_factor * x);
-                mw = (a.low[j] + a.high[j] * ex) / (1.0 + ex);
-                a.mw_out[j] = mw;
-            }
-            a.x_out[j] = x;
-            if (a.reg.constraint == GI_CONSTRAINT_MANDATORY && a.mw_out != a.x_out) a.mw_out[j] = mw;
-        }
-        a.p[j] = p;
-        k_after = p * p;
-    }
-    // deterministic grid reduction: per-CTA partials, last CTA sums them in index order
-    um = block_sum(um, scratch);
-    k_after = block_sum(k_after, scratch);
-    k_before = block_sum(k_before, scratch);
-    if (threadIdx.x == 0) {
-        a.blockpart[3 * (int64_t)blockIdx.x + 0] = um;
-        a.blockpart[3 * (int64_t)blockIdx.x + 1] = k_after;
-        a.blockpart[3 * (int64_t)blockIdx.x + 2] = k_before;
-        __threadfence();
-        const unsigned int t = atomicAdd(a.counter, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double s0 = 0, s1 = 0, s2 = 0;
-        for (int64_t b = threadIdx.x; b < gridDim.x; b += kUpdThreads) {
-            s0 += __ldcg(a.blockpart + 3 * b + 0);
-            s1 += __ldcg(a.blockpart + 3 * b + 1);
-            s2 += __ldcg(a.blockpart + 3 * b + 2);
-        }
-        s0 = block_sum(s0, scratch);
-        s1 = block_sum(s1, scratch);
-        s2 = block_sum(s2, scratch);
-        if (threadIdx.x == 0) {
-            if (!a.grad_in) a.sums[2] = s0;
-            a.sums[3] = 0.5 * s1;  // hmc.py:44-50 with the identity inverse mass
-            a.sums[4] = 0.5 * s2;
-            *a.counter = 0;
-        }
-    }
-}
-
 // mw = mw(x) for the start state
 __global__ void transform_kernel(const double *__restrict__ x, const double *__restrict__ low,
                                  const double *__restrict__ high, double log_factor, int64_t M,
@@ -373,84 +225,6 @@ __global__ void transform_kernel(const double *__restrict__ x, const double *__r
     mw[j] = (low[j] + high[j] * ex) / (1.0 + ex);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Metropolis test + state commit (hmc.py:156-173)
-// ---------------------------------------------------------------------------------------------
-struct DevState {
-    double U, Ud, Um;  // current state
-    gi_hmc_result res;
-    double u;  // uniform draw for the next test
-};
-
-__global__ void metropolis_kernel(DevState *st, const double *__restrict__ sums, double alpha, int L,
-                                  int force_accept) {
-    const double Ud = sums[1], Um = sums[2], Knew = sums[3], K0 = sums[4];
-    const double Unew = Ud + alpha * Um;  // potential.py:842
-    const double Hcur = K0 + st->U, Hnew = Knew + Unew;
-    // hmc.py:167  Hnew < Hcur or u < exp(-(Hnew - Hcur))
-    const bool acc = force_accept || (Hnew < Hcur) || (st->u < exp(-(Hnew - Hcur)));
-    if (acc) { st->U = Unew; st->Ud = Ud; st->Um = Um; }
-    st->res.accept = acc ? 1 : 0;
-    st->res.L = L;
-    st->res.U = st->U; st->res.U_data = st->Ud; st->res.U_model = st->Um;
-    st->res.Hcur = Hcur; st->res.Hnew = Hnew;
-    st->res.Unew = Unew; st->res.Unew_data = Ud; st->res.Unew_model = Um;
-}
-
-__global__ void commit_kernel(const DevState *__restrict__ st, int64_t M, int64_t N,
-                              const double *__restrict__ x, const double *__restrict__ mw,
-                              const double *__restrict__ g, const double *__restrict__ d,
-                              double *__restrict__ x_cur, double *__restrict__ mw_cur,
-                              double *__restrict__ g_cur, double *__restrict__ d_cur) {
-    if (!st->res.accept) return;
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < M) {
-        x_cur[j] = x[j];
-        g_cur[j] = g[j];
-        if (mw_cur != x_cur) mw_cur[j] = mw[j];
-    }
-    if (j < N) d_cur[j] = d[j];
-}
-
-// ---------------------------------------------------------------------------------------------
-// device RNG for throughput runs: Philox4x32-10 + Box-Muller (not numpy-compatible)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-}
-
-__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-    // uniform in (0, 1): 53 random bits, never exactly 0
-    const uint64_t v = (((uint64_t)a << 32) | b) >> 11;
-    return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
-}
-
-__global__ void philox_normal_kernel(uint64_t seed, uint64_t counter, double sigma, int64_t M,
-                                     double *__restrict__ p, DevState *st) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 2 normals per thread
-    uint32_t c[4] = {(uint32_t)t, (uint32_t)(t >> 32), (uint32_t)counter, (uint32_t)(counter >> 32)};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double u1 = u53(c[0], c[1]), u2 = u53(c[2], c[3]);
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, co;
-    sincospi(2.0 * u2, &s, &co);
-    const int64_t j = 2 * t;
-    if (j < M) p[j] = rad * co * sigma;
-    if (j + 1 < M) p[j + 1] = rad * s * sigma;
-    if (t == 0 && st) {
-        uint32_t c2[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)counter, (uint32_t)(counter >> 32)};
-        philox4x32_10(c2, (uint32_t)seed, (uint32_t)(seed >> 32));
-        st->u = u53(c2[0], c2[1]);
-    }
-}
-
 }  // namespace gi
 
 using namespace gi;
@@ -458,18 +232,6 @@ using namespace gi;
 // =============================================================================================
 // plan
 // =============================================================================================
-struct gi_plan {
-    int64_t nrows, M, ld;
-    int32_t nchains;
-    int fwd_R;
-    int64_t fwd_chunk, fwd_nchunks, fwd_rowblocks;
-    int64_t adj_rows, adj_nchunks, adj_strips;
-    int64_t upd_blocks;
-    double *fwd_part, *adj_part, *blockpart;
-    unsigned int *counter;
-    int64_t workspace_bytes;
-};
-
 static int plan_tiles(gi_plan *p) {
     const int sms = sm_count();
     const int64_t target = 32LL * 2 * sms;  // >= 32 waves of 2 CTAs/SM: tail effect < ~3 %
@@ -498,7 +260,7 @@ static int plan_tiles(gi_plan *p) {
 extern "C" int gi_plan_create(int64_t nrows, int64_t M, int64_t ld, int32_t nchains, gi_plan **out) {
     GI_REQUIRE(out, "gi_plan_create: null out");
     GI_REQUIRE(nrows > 0 && M > 0 && ld >= M && ld % 4 == 0, "gi_plan_create: bad shape");
-    GI_REQUIRE(nchains == 1, "gi_plan_create: only nchains == 1 is supported by this build");
+    GI_REQUIRE(nchains >= 1 && nchains <= 64, "gi_plan_create: 1..64 chains per plan");
     gi_plan *p = new gi_plan();
     memset(p, 0, sizeof(*p));
     p->nrows = nrows; p->M = M; p->ld = ld; p->nchains = nchains;
@@ -516,6 +278,13 @@ extern "C" int gi_plan_create(int64_t nrows, int64_t M, int64_t ld, int32_t ncha
         return cuda_fail(e, "plan workspace", __FILE__, __LINE__);
     }
     p->workspace_bytes = (int64_t)(b_fwd + b_adj + b_blk);
+    if (nchains > 1) {
+        int rc = batched_plan_init(p);
+        if (rc) {
+            gi_plan_destroy(p);
+            return rc;
+        }
+    }
     *out = p;
     return GI_OK;
 }
@@ -526,6 +295,7 @@ extern "C" int gi_plan_destroy(gi_plan *p) {
     cudaFree(p->adj_part);
     cudaFree(p->blockpart);
     cudaFree(p->counter);
+    batched_plan_free(p);
     delete p;
     return GI_OK;
 }
@@ -599,7 +369,7 @@ extern "C" int gi_gemv_adj(gi_plan *p, const double *G, const double *r, double 
     return GI_OK;
 }
 
-static int check_reg(const gi_reg_params *reg, int64_t M) {
+int gi::check_reg(const gi_reg_params *reg, int64_t M) {
     GI_REQUIRE(reg, "null regulariser parameters");
     GI_REQUIRE(reg->reg_kind >= GI_REG_DAMPING && reg->reg_kind <= GI_REG_TV,
                "Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.");
@@ -619,6 +389,7 @@ static int launch_update(gi_plan *p, const gi_reg_params *reg, const double *gra
                          double *mw_out, double *grad_out, double pcoef, double dt, int advance,
                          double *sums, cudaStream_t s) {
     UpdateArgs a;
+    a.save_k0 = 0;
     a.grad_in = grad_in; a.gpart = gpart; a.gparts = gparts;
     a.x_in = x_in; a.mw_in = mw_in; a.mwapr = mwapr; a.wmsq = wmsq; a.low = low; a.high = high;
     a.p = pm; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;

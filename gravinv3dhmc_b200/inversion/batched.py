@@ -1,0 +1,208 @@
+"""Batched chains: what the reference does with `mpiexec -n C python main_*.py` (one OS process per
+chain, each holding its own copy of Aw; example/uniformgrid/run_main.sh:18, main_uniform.py:20-22)
+runs here as ONE device-resident loop in which the C chains are columns of a dense FP64 contraction
+(`gi_hmcb_*`, DMMA tensor cores): Aw is streamed once per pass for all chains.
+
+`HMCSampleBatch(...)` takes the arguments of `hmc.HMCSample` plus `nchains`; chain c behaves exactly
+like the reference process with `myrank=c`: RNG stream `RandomState(seed + c)` consumed in the
+reference's order (randint, randn, rand per proposal; hmc.py:297,95,165), output folder
+`save_folder + str(c)` with the same `misfit.dat` / `model.dat`, and it stops being recorded once it
+has `ndraws + nsamples` accepted proposals (hmc.py:295).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+from .. import _lib
+from ._engine import reg_params
+
+
+class HMCBatch:
+    def __init__(self, model, nchains, delta, Lrange, initial_model, aprior_model, boundaries,
+                 constraint, log_factor, dobs, RegulFactor, regularization, beta, seed, Sigma,
+                 save_folder="mychain", rng="numpy", quiet=False):
+        if constraint not in _lib.CONSTRAINTS:
+            raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
+        if regularization not in _lib.REG_KINDS:
+            raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
+        if not 2 <= int(nchains) <= 64:
+            raise ValueError("HMCBatch: 2..64 chains per batch (use hmc.HMCSample for one chain)")
+        if getattr(model, "world", 1) > 1:
+            raise NotImplementedError("row-sharded batches are driven by ShardedBatch")
+        if model.wavelet:
+            raise NotImplementedError("the wavelet-compressed forward is a single-chain path")
+        if regularization in ("Smoothness", "TV") and int(np.prod(model.mshape)) != model.M:
+            raise ValueError("Smoothness/TV are defined on the full (nz, ny, nx) grid and cannot "
+                             "be used with a topography-carved model")
+        self.model, self.nchains = model, int(nchains)
+        self.dt, self.Lrange, self.Sigma = delta, Lrange, Sigma
+        self.constraint, self.log_factor = constraint, log_factor
+        self.RegulFactor, self.regularization, self.beta = RegulFactor, regularization, beta
+        self.seed, self.rng, self.quiet = seed, rng, quiet
+        self.save_folder = save_folder
+        boundaries = np.asarray(boundaries, dtype=np.float64)
+        _, WmInv, Wm = model.kernelw()
+        self.wminv = WmInv.diagonal()
+        self.low = Wm @ boundaries[:, 0]            # hmc.py:391-393
+        self.high = Wm @ boundaries[:, 1]
+        self.initial_model = Wm @ np.asarray(initial_model, dtype=np.float64)
+        self.aprior_model = Wm @ np.asarray(aprior_model, dtype=np.float64)
+        self.dobs = np.asarray(dobs, dtype=np.float64)
+        self.streams = [np.random.RandomState(seed + c) for c in range(self.nchains)]
+        self.proposals = [[] for _ in range(self.nchains)]
+        self._philox_counter = 0
+        self._h = None
+        _lib.require_cuda()
+        L = _lib.lib()
+        m = model
+        reg = reg_params(regularization, constraint, m.mshape, RegulFactor, beta, log_factor)
+        cfg = _lib.HmcConfig(m.n_total, m.M, m.ld, 1 if m.fixed else 0, 0, reg)
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self._host = dict(dobs=f(m.dobs), low=f(self.low), high=f(self.high),
+                          apr=f(self.aprior_model), wmsq=f(m.WmSquare.diagonal()))
+        fix = f(m.grav_fix) if m.fixed else None
+        h = C.c_void_p()
+        _lib.check(L.gi_hmcb_create(C.byref(cfg), self.nchains, _lib.ptr(m.Aw_pad),
+                                    _lib.ptr(self._host["dobs"]), _lib.ptr(fix),
+                                    _lib.ptr(self._host["low"]), _lib.ptr(self._host["high"]),
+                                    _lib.ptr(self._host["apr"]), _lib.ptr(self._host["wmsq"]),
+                                    _lib.stream_ptr(), C.byref(h)), "gi_hmcb_create")
+        self._h = h
+        mw = self.initial_model
+        if constraint == "logarithmic":     # hmc.py:271-273
+            x0 = (1 / log_factor) * np.log((mw - self.low) / (self.high - mw))
+        else:
+            x0 = mw
+        self.x = np.ascontiguousarray(np.tile(x0, (self.nchains, 1)))
+        _lib.check(L.gi_hmcb_set_state(self._h, _lib.ptr(self.x)), "gi_hmcb_set_state")
+
+    def close(self):
+        if self._h is not None:
+            _lib.lib().gi_hmcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def propose(self, active=None, trace=None):
+        """One proposal on every active chain (hmc.py:297-300 for each of them).  Returns the list
+        of `gi_hmc_result`-like tuples (accept, L, U, U_data, U_model) per chain (None if inactive)
+        and refreshes `self.x` for accepted chains."""
+        nc, M = self.nchains, self.model.M
+        lib = _lib.lib()
+        act = [True] * nc if active is None else list(active)
+        Ls = np.zeros(nc, dtype=np.int32)
+        res = (_lib.HmcResult * nc)()
+        if self.rng == "philox":
+            rs = np.random.RandomState(self.seed + 7919 * (self._philox_counter + 1))
+            for c in range(nc):
+                if act[c]:
+                    Ls[c] = rs.randint(self.Lrange[0], self.Lrange[1] + 1)
+            if trace is not None:
+                raise ValueError("tracing needs injected draws (rng='numpy')")
+            _lib.check(lib.gi_hmcb_propose_philox(self._h, int(self.seed), self._philox_counter,
+                                                  float(self.Sigma), _lib.ptr(Ls), float(self.dt),
+                                                  res), "gi_hmcb_propose_philox")
+            self._philox_counter += 1
+        else:
+            p0 = np.zeros((nc, M))
+            u = np.zeros(nc)
+            for c in range(nc):
+                if not act[c]:
+                    continue
+                rs = self.streams[c]
+                Ls[c] = rs.randint(self.Lrange[0], self.Lrange[1] + 1)   # hmc.py:297
+                p0[c] = rs.randn(M) * self.Sigma                          # hmc.py:95
+                u[c] = rs.rand()                                          # hmc.py:165
+            tx = tu = None
+            if trace is not None:
+                Lmax = int(Ls.max())
+                tx = np.zeros((Lmax + 1, nc, M))
+                tu = np.zeros((Lmax + 1, nc))
+            _lib.check(lib.gi_hmcb_propose(self._h, _lib.ptr(p0), _lib.ptr(Ls), float(self.dt),
+                                           _lib.ptr(u), res, _lib.ptr(tx), _lib.ptr(tu)),
+                       "gi_hmcb_propose")
+            if trace is not None:
+                trace.update(x=tx, U=tu, L=Ls.copy(),
+                             Hcur=np.array([r.Hcur for r in res]), Hnew=np.array([r.Hnew for r in res]))
+        out = []
+        any_accept = False
+        for c in range(nc):
+            if not act[c]:
+                out.append(None)
+                continue
+            r = res[c]
+            self.proposals[c].append((int(Ls[c]), bool(r.accept)))
+            any_accept |= bool(r.accept)
+            out.append((bool(r.accept), int(Ls[c]), r.U, r.U_data, r.U_model))
+        if any_accept:
+            _lib.check(lib.gi_hmcb_get_state(self._h, _lib.ptr(self.x), None, None),
+                       "gi_hmcb_get_state")
+        return out
+
+    def sample(self, nsamples, ndraws, max_proposals=None):
+        """hmc.py:252-343 for every chain of the batch."""
+        nc = self.nchains
+        folders = [self.save_folder + str(c) for c in range(nc)]
+        for fo in folders:
+            if not os.path.exists(fo):
+                os.mkdir(fo)
+            if os.path.exists(fo + "/model.dat"):
+                os.remove(fo + "/model.dat")
+        data_size, model_size = self.dobs.shape[0], self.initial_model.shape[0]
+        alpha = self.RegulFactor
+        count = [0] * nc      # accepted proposals (the reference's i)
+        ntried = 0
+        while min(count) < ndraws + nsamples:
+            if max_proposals is not None and ntried >= max_proposals:
+                break
+            active = [count[c] < ndraws + nsamples for c in range(nc)]
+            out = self.propose(active)
+            ntried += 1
+            for c in range(nc):
+                if out[c] is None:
+                    continue
+                acc, L, U, Ud, Um = out[c]
+                Udn, Umn = Ud / data_size, Um / model_size
+                Un = Udn + alpha * Umn
+                if acc:
+                    if count[c] >= ndraws:
+                        with open(folders[c] + "/misfit.dat", "a") as f:
+                            np.savetxt(f, np.array([[U, Ud, Um, Un, Udn, Umn, alpha]]), fmt="%.8f",
+                                       delimiter=" ")
+                        x = self.x[c]
+                        if self.constraint == "logarithmic":
+                            mw = (self.low + self.high * np.e ** (self.log_factor * x)) / \
+                                 (1 + np.e ** (self.log_factor * x))
+                        else:
+                            mw = x
+                        with open(folders[c] + "/model.dat", "a") as f:
+                            np.savetxt(f, (self.wminv * mw)[None, :], fmt="%.8f", delimiter=" ")
+                    count[c] += 1
+                if not self.quiet:
+                    print("chain {}: {:.2%}, misfit(total, data, alpha, model)=({:.7f},{:.7f},{:.2f},"
+                          "{:.7f}) -- accept ratio {:.2%}\n".format(
+                              c, count[c] / (ndraws + nsamples), Un, Udn, alpha, Umn,
+                              count[c] / len(self.proposals[c])))
+                    sys.stdout.flush()
+        return self.x
+
+
+def HMCSampleBatch(model, nchains, nsamples, ndraws, delta, Lrange, initial_model, aprior_model,
+                   boundaries, constraint, log_factor, dobs, adaptiveRegul, RegulRate, RegulFactor,
+                   regularization, beta, seed, Sigma, nbest=100, save_folder="mychain", rng="numpy",
+                   quiet=False, max_proposals=None):
+    """`hmc.HMCSample` for ranks 0..nchains-1 at once (argument order of hmc.py:358-361, with
+    `nchains` inserted after `model` and `myrank` implied by the chain index)."""
+    batch = HMCBatch(model, nchains, delta, Lrange, initial_model, aprior_model, boundaries,
+                     constraint, log_factor, dobs, RegulFactor, regularization, beta, seed, Sigma,
+                     save_folder=save_folder, rng=rng, quiet=quiet)
+    batch.sample(nsamples, ndraws, max_proposals=max_proposals)
+    return batch

@@ -16,6 +16,9 @@
  *                               :812-845 misfit_and_grad and the body of
  *                               inversion/hmc.py:85-177 _leapfrog
  *   gi_hmc_*                 <- inversion/hmc.py:85-177 _leapfrog, :252-343 sample (one proposal)
+ *   gi_gemm_* / gi_*_batched / gi_hmcb_*
+ *                            <- the same lines for a batch of chains (the reference runs one process
+ *                               per chain: example/uniformgrid/run_main.sh:18)
  *   gi_dwt_db4_* / gi_csr_spmv
  *                            <- gravmag/compressor1D.py:45-60, compressor3D.py:47-68 modelcompressor
  *
@@ -188,6 +191,65 @@ int gi_hmc_leapfrog_steps(gi_hmc *h, const double *p0_dev, int32_t nsteps, doubl
 /* kernels launched by this handle since creation */
 int64_t gi_hmc_launch_count(const gi_hmc *h);
 void *gi_hmc_stream(const gi_hmc *h);
+
+/* ---- C independent chains batched as columns (FP64 tensor-core contractions) ----------------- */
+/* The reference runs one OS process per chain (example/run_main.sh:18 `mpiexec -n 2`), each with its
+ * own copy of Aw; here up to 64 chains share one pass over Aw: D = Aw X, Gt = Aw^T R as DMMA
+ * (mma.sync m8n8k4 f64) contractions.  Per-chain vectors are chain-major: X, P, grad [Cp][ld];
+ * D [Cp][nrows]; R [Cp][npad]; sums [Cp][8], where Cp >= nchains and npad >= nrows are the padded
+ * sizes reported by gi_plan_batch_info (padding chains/rows must be zero-filled by the caller).
+ * A plan created with nchains > 1 serves these entry points (ld must be a multiple of 32). */
+int gi_plan_batch_info(const gi_plan *plan, int32_t *padded_chains, int64_t *padded_rows);
+/* D[c][l] = sum_k G[l][k] X[c][k] */
+int gi_gemm_fwd(gi_plan *plan, const double *G_dev, const double *X_dev, double *D_dev, void *stream);
+/* sums[c][0] = sum_l (D[c][l] + fix[l]) */
+int gi_data_sum_batched(gi_plan *plan, const double *D_dev, const double *fix_dev, double *sums_dev,
+                        void *stream);
+/* R[c][l] = (D[c][l] + fix[l] - sums[c][0]/n_total) - dobs_c[l];  sums[c][1] = sum_l R[c][l]^2 */
+int gi_residual_batched(gi_plan *plan, const double *D_dev, const double *fix_dev,
+                        const double *dobs_c_dev, int64_t n_total, double *R_dev, double *sums_dev,
+                        void *stream);
+/* Gt[c][k] = sum_l G[l][k] R[c][l] */
+int gi_gemm_adj(gi_plan *plan, const double *G_dev, const double *R_dev, double *Gt_dev, void *stream);
+/* gi_update for every chain of the batch.  The gradient is grad_in_dev ([Cp][ld], complete) when
+ * given, else 2*gdata + alpha*dR.  Chain c at trajectory step `step` (L_dev[c] = its trajectory
+ * length): step < L: p -= dt*grad, x += dt*p, clamp;  step == L: p -= dt/2*grad, grad_out written;
+ * step > L: frozen; step == 0: opening half step (mode 3 below); L == 0: the chain is inactive
+ * (frozen throughout).  With L_dev == NULL every chain takes uniform_mode (0 full step, 1 final half
+ * step, 2 frozen, 3 opening half step + advance, which also parks K before the update in sums[c][5]).
+ * low/high/mwapr/wmsq are shared [ld] vectors.  sums[c][2] = Um, [3] = K after, [4] = K before. */
+int gi_update_batched(gi_plan *plan, const gi_reg_params *reg, const double *grad_in_dev,
+                      const double *gdata_dev, const double *x_in_dev, const double *mw_in_dev,
+                      const double *mwapr_dev, const double *wmsq_dev, const double *low_dev,
+                      const double *high_dev, double *p_dev, double *x_out_dev, double *mw_out_dev,
+                      double *grad_out_dev, double dt, const int32_t *L_dev, int32_t step,
+                      int32_t uniform_mode, double *sums_dev, void *stream);
+
+/* Device-resident sampler for a batch of 2..64 chains (same roles as gi_hmc_*; host arrays are
+ * chain-major and un-padded: x [nchains][M], d [nchains][N], p0 [nchains][M]). */
+typedef struct gi_hmcb gi_hmcb;
+int gi_hmcb_create(const gi_hmc_config *cfg, int32_t nchains, const double *G_dev,
+                   const double *dobs_host, const double *gravfix_host, const double *low_host,
+                   const double *high_host, const double *mwapr_host, const double *wmsq_host,
+                   void *stream, gi_hmcb **out);
+int gi_hmcb_destroy(gi_hmcb *h);
+int gi_hmcb_set_reg(gi_hmcb *h, const gi_reg_params *reg);
+int gi_hmcb_set_state(gi_hmcb *h, const double *x_host);
+int gi_hmcb_get_state(gi_hmcb *h, double *x_host, double *d_host, double *mw_host);
+int gi_hmcb_get_misfit(gi_hmcb *h, double *U, double *U_data, double *U_model, double *grad_host);
+/* one proposal per chain with injected draws; chain c runs L_host[c] leapfrog steps (chains whose
+ * trajectory is shorter than the longest one idle; L = 0 sits the proposal out).  results[nchains]; optional traces
+ * trace_x_host [(Lmax+1)][nchains][M], trace_U_host [(Lmax+1)][nchains] (entries past L_c repeat). */
+int gi_hmcb_propose(gi_hmcb *h, const double *p0_host, const int32_t *L_host, double dt,
+                    const double *u_host, gi_hmc_result *results, double *trace_x_host,
+                    double *trace_U_host);
+/* device draws: chain c uses the Philox key seed + c (like the reference's seed + myrank) */
+int gi_hmcb_propose_philox(gi_hmcb *h, uint64_t seed, uint64_t counter, double sigma,
+                           const int32_t *L_host, double dt, gi_hmc_result *results);
+/* benchmark helper: nsteps leapfrog steps of every chain, no Metropolis; p0_dev is [Cp][ld] or NULL */
+int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t nsteps, double dt);
+int64_t gi_hmcb_launch_count(const gi_hmcb *h);
+int32_t gi_hmcb_padded_chains(const gi_hmcb *h);
 
 /* ---- wavelet-compressed forward (compressor1D/3D.py) -------------------------------------- */
 /* level-2 db4 periodization DWT of a length-n vector packed like pywt.coeffs_to_array:
