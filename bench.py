@@ -269,25 +269,28 @@ def gpu_arm(args):
     nch = args.chains
     bt = None
     # ---- the timed region: K leapfrog steps of every chain, everything resident in HBM ----
-    if world == 1 and nch > 1:
+    if nch > 1:
         from gravinv3dhmc_b200.inversion import batched
         bt = batched.HMCBatch(model, nch, HMC["delta"], HMC["Lrange"], np.full(M, HMC["init"]),
                               np.full(M, HMC["init"]), b, "mandatory", 1000, dobs, HMC["RegulFactor"],
                               HMC["regularization"], HMC["beta"], HMC["seed"], HMC["Sigma"],
                               save_folder=os.path.join(tempfile.gettempdir(), "gi_bench_chain"),
                               quiet=True)
-        cp = int(lib.gi_hmcb_padded_chains(bt._h))
+        cp = int(lib.gi_hmcb_padded_chains(bt._h)) if world == 1 else bt._sh.eng.Cp
         gen = torch.Generator(device=dev)
         gen.manual_seed(HMC["seed"])
         p0b = torch.zeros((cp, model.ld), dtype=torch.float64, device=dev)
         p0b[:nch, :M] = torch.randn((nch, M), dtype=torch.float64, device=dev, generator=gen) * HMC["Sigma"]
 
         def run_steps(k):
-            _lib.check(lib.gi_hmcb_leapfrog_steps(bt._h, _lib.ptr(p0b), int(k), float(dt)),
-                       "gi_hmcb_leapfrog_steps")
+            if world == 1:
+                _lib.check(lib.gi_hmcb_leapfrog_steps(bt._h, _lib.ptr(p0b), int(k), float(dt)),
+                           "gi_hmcb_leapfrog_steps")
+            else:
+                bt._sh.leapfrog_steps(p0b, k)
 
         def launch_count():
-            return int(lib.gi_hmcb_launch_count(bt._h))
+            return int(lib.gi_hmcb_launch_count(bt._h)) if world == 1 else int(bt._sh.eng.launches)
     elif world == 1:
         chain._ensure_handle(alpha)
         chain._sync_state(x0)
@@ -299,7 +302,6 @@ def gpu_arm(args):
         def launch_count():
             return int(lib.gi_hmc_launch_count(chain._h))
     else:
-        nch = 1
         reg = reg_params(HMC["regularization"], "mandatory", model.mshape, alpha, HMC["beta"], 1000)
         st = sharded._ShardState(chain, alpha)
         sharded._set_state(st, chain, reg, x0)
@@ -403,7 +405,7 @@ def gpu_arm(args):
 
     # ---- e2e: the public per-proposal call with host buffers (momentum in, state out) ----
     e2e = None
-    if world == 1 and nch > 1:
+    if nch > 1:
         # public batched call: per proposal the host draws L, p0 (randn) and u for every chain in the
         # reference's RNG order, p0 goes host->device, accepted states come back device->host
         done, nprop = 0, 0
@@ -415,6 +417,10 @@ def gpu_arm(args):
             nprop += 1
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            t_e2e = float(t[0])
         steps_done = sum(L for c in range(nch) for (L, _) in bt.proposals[c])
         e2e = {"value": steps_done / t_e2e, "unit": "leapfrog steps/s",
                "h2d_bytes_per_step": int(nprop * nch * (8 * M + 12) / steps_done),

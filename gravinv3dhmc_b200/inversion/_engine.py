@@ -119,3 +119,110 @@ class BlockEngine:
         mw = (low + high * e) / (1 + e)
         mw[self.M:] = 0
         return mw
+
+
+class BatchEngine:
+    """One row shard, C chains batched as columns (gi_gemm_fwd / gi_data_sum_batched /
+    gi_residual_batched / gi_gemm_adj / gi_update_batched).  Per gradient evaluation of the batch:
+
+        D_g = Aw_g X          local rows, all chains        (DMMA contraction)
+        all-reduce(sum D)     Cp doubles
+        R_g, |R_g|^2          local
+        Gt_g = Aw_g^T R_g     local partial [Cp][ld]        (DMMA contraction)
+        all-reduce(Gt, |R|^2) Cp*ld + Cp doubles            (one NCCL call)
+        update                replicated on every rank (NCCL returns identical bits everywhere)
+    """
+
+    def __init__(self, Aw_pad, M, nchains, dobs_local, dobs_mean, n_total, gravfix_local=None,
+                 group=None):
+        self.torch = torch = _lib.require_cuda()
+        self.L = _lib.lib()
+        self.Aw = Aw_pad
+        self.dev = Aw_pad.device
+        self.n_local, self.ld = (int(v) for v in Aw_pad.shape)
+        self.M, self.nchains, self.n_total, self.group = int(M), int(nchains), int(n_total), group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+
+            self.world = dist.get_world_size(group)
+        self.plan = C.c_void_p()
+        _lib.check(self.L.gi_plan_create(self.n_local, self.M, self.ld, self.nchains,
+                                         C.byref(self.plan)), "gi_plan_create")
+        cp, npad = C.c_int32(), C.c_int64()
+        _lib.check(self.L.gi_plan_batch_info(self.plan, C.byref(cp), C.byref(npad)),
+                   "gi_plan_batch_info")
+        self.Cp, self.npad = cp.value, npad.value
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        dl = np.asarray(dobs_local, dtype=np.float64)
+        self.dobs_c = torch.as_tensor(dl - dobs_mean, **f64)
+        self.fix = None
+        if gravfix_local is not None:
+            self.fix = torch.as_tensor(np.asarray(gravfix_local, dtype=np.float64), **f64)
+        self.d = torch.zeros((self.Cp, self.n_local), **f64)
+        self.r = torch.zeros((self.Cp, self.npad), **f64)
+        # gradient partials + Cp trailing slots: one all-reduce carries Gt and sum r^2
+        self.gext = torch.zeros(self.Cp * self.ld + self.Cp, **f64)
+        self.g = self.gext[: self.Cp * self.ld].view(self.Cp, self.ld)
+        self.sums = torch.zeros((self.Cp, 8), **f64)
+        self.s0 = torch.zeros(self.Cp, **f64)
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.L.gi_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    def mat(self, a=None):
+        """zero-padded device [Cp][ld] matrix; `a` is [nchains][M] (numpy)"""
+        t = self.torch.zeros((self.Cp, self.ld), dtype=self.torch.float64, device=self.dev)
+        if a is not None:
+            t[: self.nchains, : self.M] = self.torch.as_tensor(
+                np.ascontiguousarray(a, dtype=np.float64), device=self.dev)
+        return t
+
+    def vec(self, a=None):
+        t = self.torch.zeros(self.ld, dtype=self.torch.float64, device=self.dev)
+        if a is not None:
+            t[: self.M] = self.torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.dev)
+        return t
+
+    def _all_reduce(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def data_pass(self, MW):
+        """D, R, Ud and Gt = Aw^T R for the padded [Cp][ld] device matrix MW"""
+        L, s, p = self.L, _lib.stream_ptr(), _lib.ptr
+        _lib.check(L.gi_gemm_fwd(self.plan, p(self.Aw), p(MW), p(self.d), s), "gi_gemm_fwd")
+        _lib.check(L.gi_data_sum_batched(self.plan, p(self.d), p(self.fix), p(self.sums), s),
+                   "gi_data_sum_batched")
+        if self.world > 1:
+            self.s0.copy_(self.sums[:, 0])
+            self._all_reduce(self.s0)
+            self.sums[:, 0] = self.s0
+        _lib.check(L.gi_residual_batched(self.plan, p(self.d), p(self.fix), p(self.dobs_c),
+                                         self.n_total, p(self.r), p(self.sums), s),
+                   "gi_residual_batched")
+        _lib.check(L.gi_gemm_adj(self.plan, p(self.Aw), p(self.r), p(self.g), s), "gi_gemm_adj")
+        if self.world > 1:
+            self.gext[self.Cp * self.ld:] = self.sums[:, 1]
+            self._all_reduce(self.gext)
+            self.sums[:, 1] = self.gext[self.Cp * self.ld:]
+        self.launches += 6
+
+    def update(self, reg, grad_in, x_in, mw_in, mwapr, wmsq, low, high, pm, x_out, mw_out, grad_out,
+               dt, L_dev, step, mode):
+        p = _lib.ptr
+        _lib.check(self.L.gi_update_batched(self.plan, C.byref(reg), p(grad_in),
+                                            None if grad_in is not None else p(self.g), p(x_in),
+                                            p(mw_in), p(mwapr), p(wmsq), p(low), p(high), p(pm),
+                                            p(x_out), p(mw_out), p(grad_out), float(dt), p(L_dev),
+                                            int(step), int(mode), p(self.sums), _lib.stream_ptr()),
+                   "gi_update_batched")
+        self.launches += 1

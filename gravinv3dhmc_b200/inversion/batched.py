@@ -21,6 +21,119 @@ from .. import _lib
 from ._engine import reg_params
 
 
+class _ShardedBatchState:
+    """Row-sharded batch (multi-GPU): replicated [Cp][ld] chain state on every rank, the kernel rows
+    split by observation; per gradient evaluation two all-reduces (Cp scalars, then Cp*ld + Cp
+    doubles), see `_engine.BatchEngine`.  Every rank draws the same numbers (same seeds) and takes
+    the same Metropolis decisions on the host from all-reduced sums."""
+
+    def __init__(self, b):
+        from ._engine import BatchEngine
+
+        m = b.model
+        lo, hi = m.rows
+        fix = np.asarray(m.grav_fix, dtype=np.float64)[lo:hi] if m.fixed else None
+        self.b = b
+        self.eng = eng = BatchEngine(m.Aw_pad, m.M, b.nchains, m.dobs[lo:hi], float(np.mean(m.dobs)),
+                                     m.n_total, fix, m.group)
+        torch = eng.torch
+        self.low, self.high, self.apr = eng.vec(b.low), eng.vec(b.high), eng.vec(b.aprior_model)
+        self.logc = b.constraint == "logarithmic"
+        self.x_cur, self.g_cur = eng.mat(b.x), eng.mat()
+        self.xa, self.xb, self.p, self.gnew = eng.mat(), eng.mat(), eng.mat(), eng.mat()
+        self.mw_cur = eng.mat() if self.logc else self.x_cur
+        self.mwa = eng.mat() if self.logc else self.xa
+        self.mwb = eng.mat() if self.logc else self.xb
+        self.d_cur = torch.zeros_like(eng.d)
+        self.L_dev = torch.zeros(eng.Cp, dtype=torch.int32, device=eng.dev)
+        self.U = np.zeros(eng.Cp)
+        self.Ud = np.zeros(eng.Cp)
+        self.Um = np.zeros(eng.Cp)
+        self._to_mw(self.x_cur, self.mw_cur)
+        # gradient and potential at the start state (hmc.py:105)
+        eng.data_pass(self.mw_cur)
+        eng.update(b.reg, None, self.x_cur, self.mw_cur, self.apr, m.wmsq_dev, self.low, self.high,
+                   self.p, self.xa, self.mwa, self.g_cur, 0.0, None, 0, 1)
+        s = eng.sums.cpu().numpy()
+        self.Ud[:], self.Um[:] = s[:, 1], s[:, 2]
+        self.U[:] = self.Ud + b.reg.alpha * self.Um
+        self.d_cur.copy_(eng.d)
+
+    def _to_mw(self, x, mw):
+        if not self.logc:
+            return
+        t, b = self.eng.torch, self.b
+        e = t.pow(t.tensor(np.e, dtype=t.float64, device=x.device), b.log_factor * x)
+        mw.copy_((self.low[None, :] + self.high[None, :] * e) / (1 + e))
+        mw[:, self.eng.M:] = 0
+
+    def leapfrog_steps(self, p0_dev, nsteps):
+        """benchmark helper (like gi_hmcb_leapfrog_steps): nsteps leapfrog steps of every chain
+        from the current state, no Metropolis test"""
+        b, eng, m = self.b, self.eng, self.b.model
+        dt = float(b.dt)
+        self.p.copy_(p0_dev)
+        self.L_dev.fill_(int(nsteps) + 1)
+        eng.update(b.reg, self.g_cur, self.x_cur, self.mw_cur, self.apr, m.wmsq_dev, self.low,
+                   self.high, self.p, self.xa, self.mwa, None, dt, self.L_dev, 0, 3)
+        xin, xout, mwin, mwout = self.xa, self.xb, self.mwa, self.mwb
+        for i in range(1, int(nsteps) + 1):
+            eng.data_pass(mwin)
+            eng.update(b.reg, None, xin, mwin, self.apr, m.wmsq_dev, self.low, self.high, self.p, xout,
+                       mwout, self.gnew, dt, self.L_dev, i, 0)
+            xin, xout = xout, xin
+            mwin, mwout = (mwout, mwin) if self.logc else (xin, xout)
+
+    def propose(self, p0, Ls, u, res, tx, tu):
+        b, eng, m = self.b, self.eng, self.b.model
+        torch = eng.torch
+        nc, M, dt, alpha = b.nchains, m.M, float(b.dt), b.reg.alpha
+        self.p.zero_()
+        self.p[:nc, :M] = torch.as_tensor(p0, device=eng.dev)
+        Lpad = np.zeros(eng.Cp, dtype=np.int32)
+        Lpad[:nc] = Ls
+        self.L_dev.copy_(torch.as_tensor(Lpad))
+        if tx is not None:
+            tx[0], tu[0] = self.x_cur[:nc, :M].cpu().numpy(), self.U[:nc]
+        eng.update(b.reg, self.g_cur, self.x_cur, self.mw_cur, self.apr, m.wmsq_dev, self.low,
+                   self.high, self.p, self.xa, self.mwa, None, dt, self.L_dev, 0, 3)
+        xin, xout, mwin, mwout = self.xa, self.xb, self.mwa, self.mwb
+        for i in range(1, int(Ls.max()) + 1):
+            eng.data_pass(mwin)
+            eng.update(b.reg, None, xin, mwin, self.apr, m.wmsq_dev, self.low, self.high, self.p, xout,
+                       mwout, self.gnew, dt, self.L_dev, i, 0)
+            if tx is not None:
+                s = eng.sums.cpu().numpy()
+                tx[i], tu[i] = xin[:nc, :M].cpu().numpy(), (s[:, 1] + alpha * s[:, 2])[:nc]
+            xin, xout = xout, xin
+            mwin, mwout = (mwout, mwin) if self.logc else (xin, xout)
+        s = eng.sums.cpu().numpy()
+        acc_idx = []
+        for c in range(nc):
+            r = res[c]
+            r.L = int(Ls[c])
+            if Ls[c] == 0:
+                r.accept = 0
+                continue
+            Ud, Um, Knew, K0 = s[c, 1], s[c, 2], s[c, 3], s[c, 5]
+            Unew = Ud + alpha * Um
+            Hcur, Hnew = K0 + self.U[c], Knew + Unew
+            acc = bool(Hnew < Hcur or u[c] < np.exp(-(Hnew - Hcur)))   # hmc.py:167
+            if acc:
+                self.U[c], self.Ud[c], self.Um[c] = Unew, Ud, Um
+                acc_idx.append(c)
+            r.accept = int(acc)
+            r.U, r.U_data, r.U_model = self.U[c], self.Ud[c], self.Um[c]
+            r.Hcur, r.Hnew, r.Unew, r.Unew_data, r.Unew_model = Hcur, Hnew, Unew, Ud, Um
+        if acc_idx:
+            idx = torch.as_tensor(acc_idx, device=eng.dev)
+            self.x_cur[idx] = xin[idx]
+            if self.logc:
+                self.mw_cur[idx] = mwin[idx]
+            self.g_cur[idx] = self.gnew[idx]
+            self.d_cur[idx] = eng.d[idx]
+
+
 class HMCBatch:
     def __init__(self, model, nchains, delta, Lrange, initial_model, aprior_model, boundaries,
                  constraint, log_factor, dobs, RegulFactor, regularization, beta, seed, Sigma,
@@ -31,8 +144,6 @@ class HMCBatch:
             raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
         if not 2 <= int(nchains) <= 64:
             raise ValueError("HMCBatch: 2..64 chains per batch (use hmc.HMCSample for one chain)")
-        if getattr(model, "world", 1) > 1:
-            raise NotImplementedError("row-sharded batches are driven by ShardedBatch")
         if model.wavelet:
             raise NotImplementedError("the wavelet-compressed forward is a single-chain path")
         if regularization in ("Smoothness", "TV") and int(np.prod(model.mshape)) != model.M:
@@ -56,11 +167,21 @@ class HMCBatch:
         self.proposals = [[] for _ in range(self.nchains)]
         self._philox_counter = 0
         self._h = None
+        self._sh = None
         _lib.require_cuda()
+        mw = self.initial_model
+        if constraint == "logarithmic":     # hmc.py:271-273
+            x0 = (1 / log_factor) * np.log((mw - self.low) / (self.high - mw))
+        else:
+            x0 = mw
+        self.x = np.ascontiguousarray(np.tile(x0, (self.nchains, 1)))
+        self.reg = reg_params(regularization, constraint, model.mshape, RegulFactor, beta, log_factor)
+        if getattr(model, "world", 1) > 1:
+            self._sh = _ShardedBatchState(self)
+            return
         L = _lib.lib()
         m = model
-        reg = reg_params(regularization, constraint, m.mshape, RegulFactor, beta, log_factor)
-        cfg = _lib.HmcConfig(m.n_total, m.M, m.ld, 1 if m.fixed else 0, 0, reg)
+        cfg = _lib.HmcConfig(m.n_total, m.M, m.ld, 1 if m.fixed else 0, 0, self.reg)
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         self._host = dict(dobs=f(m.dobs), low=f(self.low), high=f(self.high),
                           apr=f(self.aprior_model), wmsq=f(m.WmSquare.diagonal()))
@@ -72,12 +193,6 @@ class HMCBatch:
                                     _lib.ptr(self._host["apr"]), _lib.ptr(self._host["wmsq"]),
                                     _lib.stream_ptr(), C.byref(h)), "gi_hmcb_create")
         self._h = h
-        mw = self.initial_model
-        if constraint == "logarithmic":     # hmc.py:271-273
-            x0 = (1 / log_factor) * np.log((mw - self.low) / (self.high - mw))
-        else:
-            x0 = mw
-        self.x = np.ascontiguousarray(np.tile(x0, (self.nchains, 1)))
         _lib.check(L.gi_hmcb_set_state(self._h, _lib.ptr(self.x)), "gi_hmcb_set_state")
 
     def close(self):
@@ -101,6 +216,8 @@ class HMCBatch:
         Ls = np.zeros(nc, dtype=np.int32)
         res = (_lib.HmcResult * nc)()
         if self.rng == "philox":
+            if self._sh is not None:
+                raise NotImplementedError("rng='philox' is a single-GPU option")
             rs = np.random.RandomState(self.seed + 7919 * (self._philox_counter + 1))
             for c in range(nc):
                 if act[c]:
@@ -126,9 +243,12 @@ class HMCBatch:
                 Lmax = int(Ls.max())
                 tx = np.zeros((Lmax + 1, nc, M))
                 tu = np.zeros((Lmax + 1, nc))
-            _lib.check(lib.gi_hmcb_propose(self._h, _lib.ptr(p0), _lib.ptr(Ls), float(self.dt),
-                                           _lib.ptr(u), res, _lib.ptr(tx), _lib.ptr(tu)),
-                       "gi_hmcb_propose")
+            if self._sh is not None:
+                self._sh.propose(p0, Ls, u, res, tx, tu)
+            else:
+                _lib.check(lib.gi_hmcb_propose(self._h, _lib.ptr(p0), _lib.ptr(Ls), float(self.dt),
+                                               _lib.ptr(u), res, _lib.ptr(tx), _lib.ptr(tu)),
+                           "gi_hmcb_propose")
             if trace is not None:
                 trace.update(x=tx, U=tu, L=Ls.copy(),
                              Hcur=np.array([r.Hcur for r in res]), Hnew=np.array([r.Hnew for r in res]))
@@ -143,15 +263,19 @@ class HMCBatch:
             any_accept |= bool(r.accept)
             out.append((bool(r.accept), int(Ls[c]), r.U, r.U_data, r.U_model))
         if any_accept:
-            _lib.check(lib.gi_hmcb_get_state(self._h, _lib.ptr(self.x), None, None),
-                       "gi_hmcb_get_state")
+            if self._sh is not None:
+                self.x[:] = self._sh.x_cur[:nc, :M].cpu().numpy()
+            else:
+                _lib.check(lib.gi_hmcb_get_state(self._h, _lib.ptr(self.x), None, None),
+                           "gi_hmcb_get_state")
         return out
 
     def sample(self, nsamples, ndraws, max_proposals=None):
         """hmc.py:252-343 for every chain of the batch."""
         nc = self.nchains
         folders = [self.save_folder + str(c) for c in range(nc)]
-        for fo in folders:
+        writes = getattr(self.model, "rank", 0) == 0
+        for fo in folders if writes else []:
             if not os.path.exists(fo):
                 os.mkdir(fo)
             if os.path.exists(fo + "/model.dat"):
@@ -173,7 +297,7 @@ class HMCBatch:
                 Udn, Umn = Ud / data_size, Um / model_size
                 Un = Udn + alpha * Umn
                 if acc:
-                    if count[c] >= ndraws:
+                    if count[c] >= ndraws and writes:
                         with open(folders[c] + "/misfit.dat", "a") as f:
                             np.savetxt(f, np.array([[U, Ud, Um, Un, Udn, Umn, alpha]]), fmt="%.8f",
                                        delimiter=" ")

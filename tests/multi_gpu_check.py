@@ -1,0 +1,92 @@
+"""Row-sharded (multi-GPU) parity check, run under torchrun on N >= 2 GPUs of one node:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multi_gpu_check.py
+
+Every rank assembles its observation rows, the chains run through the NCCL all-reduce path
+(single chain: inversion/sharded.py; batch: inversion/batched.py) and rank 0 compares positions,
+potentials and accept decisions with the CPU oracle (1e-9) and the weights with 1e-12.
+Also driven by tests/test_gpu_multi.py when >= 2 GPUs are visible."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    from gravinv3dhmc_b200.inversion import batched, hmc, potential
+    from oracle import oracle_np as onp
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "potential_hmc.npz"))
+    o, dobs = g["small_obs"], g["small_dobs"]
+    model = potential.GravMagModule(dobs, (0, 400, 0, 600, 0, 500), (100, 100, 100),
+                                    (o[:, 0], o[:, 1], o[:, 2]), verbose=False,
+                                    shard=(rank, world), group=dist.group.WORLD)
+    M = model.M
+    lo, hi = model.rows
+    assert np.allclose(model.Wm.diagonal(), g["small_wm"], rtol=1e-12)
+    err = np.max(np.abs(model.Aw.cpu().numpy() - g["small_Aw"][lo:hi])) / np.max(np.abs(g["small_Aw"]))
+    assert err < 1e-10, err
+    om = onp.OracleModel(g["small_Aw"], g["small_wm"], dobs, tuple(g["small_mshape"]))
+    b = np.ones((M, 2))
+    b[:, 0], b[:, 1] = -5.0, 5.0
+    tmp = tempfile.mkdtemp()
+    # ---- single chain, row-sharded ----
+    for reg in ("Damping", "TV"):
+        ch = hmc.HMCSample(model, 4, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                           "mandatory", 1000, dobs, "Fixed", 0.8, 1.0, reg, 0.001, 3, 1.0, myrank=0,
+                           save_folder=os.path.join(tmp, "s_%s_%d_" % (reg, rank)), quiet=True)
+        ref = onp.hmc_sample(om, 4, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                             "mandatory", 1000, 1.0, reg, 0.001, 3, 1.0)
+        assert [(L, bool(a)) for L, a in ch.proposals] == [(L, bool(a)) for L, a in ref["log"]], reg
+        scale = np.max(np.abs(ref["x"]))
+        assert np.max(np.abs(ch.x_final - ref["x"])) < 1e-9 * scale, reg
+    # ---- batch of chains, row-sharded ----
+    nch, nprops = 5, 5
+    bt = batched.HMCBatch(model, nch, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                          "mandatory", 1000, dobs, 1.0, "MS", 0.001, 3, 1.0,
+                          save_folder=os.path.join(tmp, "b%d_" % rank), quiet=True)
+    traces = []
+    for _ in range(nprops):
+        tr = {}
+        bt.propose(trace=tr)
+        traces.append(tr)
+    nacc = nrej = 0
+    for c in range(nch):
+        otr = []
+        onp.hmc_sample(om, 10 ** 6, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                       "mandatory", 1000, 1.0, "MS", 0.001, 3, 1.0, myrank=c, max_proposals=nprops,
+                       trace=otr)
+        assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(t["L"], bool(t["accept"])) for t in otr]
+        for k, t in enumerate(otr):
+            L = t["L"]
+            rx = np.array([x for x, _ in t["steps"]])
+            rU = np.array([U for _, U in t["steps"]])
+            gx, gU = traces[k]["x"][: L + 1, c], traces[k]["U"][: L + 1, c]
+            assert np.max(np.abs(gx - rx) / np.max(np.abs(rx), axis=1, keepdims=True)) < 1e-9
+            assert np.max(np.abs(gU - rU) / np.abs(rU)) < 1e-9
+            nacc += bool(t["accept"])
+            nrej += not t["accept"]
+    # the replicated state is bitwise identical on every rank
+    xs = [torch.zeros_like(bt._sh.x_cur) for _ in range(world)]
+    dist.all_gather(xs, bt._sh.x_cur)
+    assert all(torch.equal(xs[0], x) for x in xs)
+    dist.barrier()
+    if rank == 0:
+        print("multi_gpu_check ok: world=%d, %d accepted / %d rejected batch proposals match the oracle"
+              % (world, nacc, nrej))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
