@@ -100,6 +100,9 @@ SIGNATURES = {
     "gi_dwt_db4_l2_1d_batch": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, C.POINTER(_I64), _P]),
     "gi_dwt_db4_l2_3d_batch": (C.c_int, [_P, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, _P, _I64,
                                          C.POINTER(C.c_int32 * 3), _P]),
+    "gi_csr_count": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _P]),
+    "gi_csr_fill": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _P, _P, _P]),
+    "gi_hmc_set_wavelet": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _I64]),
     "gi_csr_spmv": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
 }
 

@@ -118,6 +118,7 @@ __global__ void fwd_reduce_kernel(const double *__restrict__ part, int64_t nrows
 //  mode 0: d = sum part; s0 = sum(d + fix); mean = s0/n_total; r = (d+fix-mean) - dobs_c; s1 = sum r^2
 //  mode 1: s0 = sum(d + fix) only (d given)
 //  mode 2: r, s1 from given d and sums[0] (already reduced over ranks)
+//  mode 3: d given (e.g. the wavelet-compressed forward): s0, r, s1
 constexpr int kFinThreads = 1024;
 __global__ void __launch_bounds__(kFinThreads)
 data_misfit_kernel(int mode, const double *__restrict__ part, int64_t nchunks, int64_t nrows,
@@ -432,6 +433,13 @@ struct gi_hmc {
     DevState *st_host;  // pinned
     bool has_state;
     int64_t launches;
+    // wavelet-compressed forward (0 = off)
+    int wv_kind, wv_nz, wv_ny, wv_nx;
+    const int64_t *wv_indptr;
+    const int32_t *wv_indices;
+    const double *wv_data;
+    int64_t wv_ncoef;
+    double *wv_coef;
 };
 
 static void hmc_free(gi_hmc *h) {
@@ -443,6 +451,7 @@ static void hmc_free(gi_hmc *h) {
         cudaFree(h->mw_cur); cudaFree(h->mwa); cudaFree(h->mwb);
     }
     cudaFree(h->st);
+    cudaFree(h->wv_coef);
     if (h->st_host) cudaFreeHost(h->st_host);
     gi_plan_destroy(h->plan);
     delete h;
@@ -549,11 +558,27 @@ static int grad_eval_and_update(gi_hmc *h, const double *x_in, const double *mw_
                                 int advance) {
     gi_plan *p = h->plan;
     cudaStream_t s = h->stream;
-    int rc = launch_fwd_partial(p, h->G, mw_in, s);
-    if (rc) return rc;
-    data_misfit_kernel<<<1, kFinThreads, 0, s>>>(0, p->fwd_part, p->fwd_nchunks, p->nrows, p->nrows,
-                                                 h->d, h->cfg.fixed ? h->fix : nullptr, h->dobs_c,
-                                                 h->r, h->sums);
+    int rc;
+    if (h->wv_kind) {
+        // d = Awcp @ DWT(mw)  (compressor1D.py:45-60 / compressor3D.py:47-68)
+        if (h->wv_kind == 1)
+            rc = gi_dwt_db4_l2_1d(mw_in, h->cfg.M, h->wv_coef, nullptr, s);
+        else
+            rc = gi_dwt_db4_l2_3d(mw_in, h->wv_nz, h->wv_ny, h->wv_nx, h->wv_coef, nullptr, s);
+        if (rc) return rc;
+        rc = gi_csr_spmv(h->wv_indptr, h->wv_indices, h->wv_data, p->nrows, h->wv_coef, h->d, s);
+        if (rc) return rc;
+        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, p->nrows, h->d,
+                                                     h->cfg.fixed ? h->fix : nullptr, h->dobs_c,
+                                                     h->r, h->sums);
+        h->launches += (h->wv_kind == 1 ? 2 : 7);
+    } else {
+        rc = launch_fwd_partial(p, h->G, mw_in, s);
+        if (rc) return rc;
+        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(0, p->fwd_part, p->fwd_nchunks, p->nrows,
+                                                     p->nrows, h->d, h->cfg.fixed ? h->fix : nullptr,
+                                                     h->dobs_c, h->r, h->sums);
+    }
     GI_LAUNCH_CHECK();
     rc = launch_adj_partial(p, h->G, h->r, s);
     if (rc) return rc;
@@ -708,6 +733,36 @@ extern "C" int gi_hmc_leapfrog_steps(gi_hmc *h, const double *p0_dev, int32_t ns
     else
         GI_CUDA(cudaMemsetAsync(h->p, 0, sizeof(double) * h->cfg.ld, s));
     return run_trajectory(h, nsteps, dt, nullptr, nullptr, nullptr, false);
+}
+
+extern "C" int gi_hmc_set_wavelet(gi_hmc *h, int32_t kind, int32_t nz, int32_t ny, int32_t nx,
+                                  const int64_t *indptr, const int32_t *indices, const double *data,
+                                  int64_t ncoef) {
+    GI_REQUIRE(h, "gi_hmc_set_wavelet: null handle");
+    GI_REQUIRE(kind == 0 || kind == 1 || kind == 3, "gi_hmc_set_wavelet: kind must be 0, 1 or 3");
+    h->has_state = false;
+    cudaFree(h->wv_coef);
+    h->wv_coef = nullptr;
+    h->wv_kind = 0;
+    if (kind == 0) return GI_OK;
+    GI_REQUIRE(indptr && indices && data && ncoef > 0, "gi_hmc_set_wavelet: null CSR arrays");
+    int64_t want = 0;
+    if (kind == 1) {
+        int rc = gi_dwt_db4_l2_1d(nullptr, h->cfg.M, nullptr, &want, nullptr);
+        if (rc) return rc;
+    } else {
+        GI_REQUIRE((int64_t)nz * ny * nx == h->cfg.M,
+                   "gi_hmc_set_wavelet: the 3-D wavelet needs the full (nz, ny, nx) grid");
+        int32_t shp[3];
+        int rc = gi_dwt_db4_l2_3d(nullptr, nz, ny, nx, nullptr, shp, nullptr);
+        if (rc) return rc;
+        want = (int64_t)shp[0] * shp[1] * shp[2];
+    }
+    GI_REQUIRE(want == ncoef, "gi_hmc_set_wavelet: CSR column count does not match the transform");
+    GI_CUDA(cudaMalloc(&h->wv_coef, sizeof(double) * ncoef));
+    h->wv_kind = kind; h->wv_nz = nz; h->wv_ny = ny; h->wv_nx = nx;
+    h->wv_indptr = indptr; h->wv_indices = indices; h->wv_data = data; h->wv_ncoef = ncoef;
+    return GI_OK;
 }
 
 extern "C" int64_t gi_hmc_launch_count(const gi_hmc *h) { return h ? h->launches : 0; }

@@ -107,6 +107,45 @@ __global__ void csr_spmv_kernel(const int64_t *__restrict__ indptr, const int32_
     if (lane == 0) y[row] = acc;
 }
 
+// ---- dense coefficient rows -> CSR (compressor*.kernelcompressor: zero |c| < thr, csr_matrix) ----
+// one warp per row; an entry is kept when !(|c| < thr) && c != 0 (scipy drops exact zeros)
+__device__ __forceinline__ bool csr_keep(double v, double thr) { return !(fabs(v) < thr) && v != 0.0; }
+
+__global__ void csr_count_kernel(const double *__restrict__ dense, int64_t nrows, int64_t ncols,
+                                 int64_t bs, double thr, int64_t *__restrict__ counts) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const double *p = dense + row * bs;
+    int n = 0;
+    for (int64_t c = lane; c < ncols; c += 32) n += csr_keep(p[c], thr) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) counts[row] = n;
+}
+
+__global__ void csr_fill_kernel(const double *__restrict__ dense, int64_t nrows, int64_t ncols,
+                                int64_t bs, double thr, const int64_t *__restrict__ indptr,
+                                int32_t *__restrict__ indices, double *__restrict__ data) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const double *p = dense + row * bs;
+    int64_t pos = indptr[row];
+    for (int64_t c0 = 0; c0 < ncols; c0 += 32) {  // ascending column order within the row
+        const int64_t c = c0 + lane;
+        const double v = c < ncols ? p[c] : 0.0;
+        const bool keep = c < ncols && csr_keep(v, thr);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int64_t at = pos + __popc(m & ((1u << lane) - 1u));
+            indices[at] = (int32_t)c;
+            data[at] = v;
+        }
+        pos += __popc(m);
+    }
+}
+
 static inline int half_up(int n) { return (n + 1) / 2; }
 
 // transform the (n0,n1,n2) sub-box of `in` (full dims d0.. ) along all three axes -> out with
@@ -224,6 +263,30 @@ extern "C" int gi_csr_spmv(const int64_t *indptr, const int32_t *indices, const 
     GI_REQUIRE(indptr && x && y, "gi_csr_spmv: null pointer");
     csr_spmv_kernel<<<(unsigned)ceil_div(nrows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         indptr, indices, data, nrows, x, y);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_csr_count(const double *dense, int64_t nrows, int64_t ncols, int64_t row_stride,
+                            double thr, int64_t *counts, void *stream) {
+    GI_REQUIRE(nrows >= 0 && ncols >= 0 && row_stride >= ncols, "gi_csr_count: bad shape");
+    if (nrows == 0) return GI_OK;
+    GI_REQUIRE(dense && counts, "gi_csr_count: null pointer");
+    csr_count_kernel<<<(unsigned)ceil_div(nrows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        dense, nrows, ncols, row_stride, thr, counts);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_csr_fill(const double *dense, int64_t nrows, int64_t ncols, int64_t row_stride,
+                           double thr, const int64_t *indptr, int32_t *indices, double *data,
+                           void *stream) {
+    GI_REQUIRE(nrows >= 0 && ncols >= 0 && ncols < (1LL << 31) && row_stride >= ncols,
+               "gi_csr_fill: bad shape");
+    if (nrows == 0) return GI_OK;
+    GI_REQUIRE(dense && indptr && indices && data, "gi_csr_fill: null pointer");
+    csr_fill_kernel<<<(unsigned)ceil_div(nrows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        dense, nrows, ncols, row_stride, thr, indptr, indices, data);
     GI_LAUNCH_CHECK();
     return GI_OK;
 }

@@ -84,11 +84,15 @@ class BlockEngine:
 
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
-    def data_pass(self, mw):
+    def data_pass(self, mw, dpre=None):
         """d, r, Ud and gdata = Aw^T r for the padded device vector `mw`; leaves the results in
-        self.d / self.r / self.g / self.sums[0:2]."""
+        self.d / self.r / self.g / self.sums[0:2].  `dpre` (device, this rank's rows) overrides the
+        dense forward product (wavelet-compressed forward, potential.py:693-696)."""
         L, s, p = self.L, _lib.stream_ptr(), _lib.ptr
-        _lib.check(L.gi_gemv_fwd(self.plan, p(self.Aw), p(mw), p(self.d), s), "gi_gemv_fwd")
+        if dpre is not None:
+            self.d.copy_(dpre)
+        else:
+            _lib.check(L.gi_gemv_fwd(self.plan, p(self.Aw), p(mw), p(self.d), s), "gi_gemv_fwd")
         _lib.check(L.gi_data_sum(self.plan, p(self.d), p(self.fix), p(self.sums), s), "gi_data_sum")
         self._all_reduce(self.sums[0:1])
         _lib.check(L.gi_residual(self.plan, p(self.d), p(self.fix), p(self.dobs_c), self.n_total,

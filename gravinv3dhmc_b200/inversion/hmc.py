@@ -73,8 +73,6 @@ class HamitonianMC:
 
     def _ensure_handle(self, alpha):
         m = self.model
-        if m.wavelet:
-            raise NotImplementedError("wavelet-compressed forward is driven by WaveletChain")
         if self.regularization in ("Smoothness", "TV") and int(np.prod(m.mshape)) != m.M:
             raise ValueError("Smoothness/TV are defined on the full (nz, ny, nx) grid and cannot "
                              "be used with a topography-carved model")
@@ -102,6 +100,12 @@ class HamitonianMC:
                    "gi_hmc_create")
         self._h = h
         self._alpha = alpha
+        if m.wavelet in ("1D", "3D"):  # potential.py:693-696: forward through the compressed kernel
+            nz, ny, nx = (int(v) for v in m.mshape)
+            cp = m.Awcp
+            _lib.check(L.gi_hmc_set_wavelet(h, 1 if m.wavelet == "1D" else 3, nz, ny, nx,
+                                            _lib.ptr(cp.indptr), _lib.ptr(cp.indices),
+                                            _lib.ptr(cp.data), cp.shape[1]), "gi_hmc_set_wavelet")
 
     def close(self):
         if self._h is not None:

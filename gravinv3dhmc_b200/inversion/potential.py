@@ -226,7 +226,8 @@ class GravMagModule:
                                        self.n_total, fix, self.group)
         return self._engine
 
-    def _forward(self, eng, mw_dev):
+    def _forward(self, mw_dev):
+        """device forward data of the wavelet-compressed kernel (None without wavelet)"""
         if self.wavelet == "1D":
             from ..gravmag import compressor1D as cp1D
             return cp1D.modelcompressor(mw_dev[: self.M], self.Awcp)
@@ -238,16 +239,13 @@ class GravMagModule:
     def _evaluate(self, mw, mwapr, alpha, regularization, beta, constraint="mandatory",
                   log_factor=0.0):
         """(U, grad, dpre, Ud, Um) at the weighted model `mw` (numpy)."""
-        if self.wavelet:
-            raise NotImplementedError("use HMCSample / data_all for the wavelet-compressed forward")
         eng = self.engine()
-        torch = eng.torch
         reg = reg_params(regularization, "mandatory", self.mshape, alpha, beta, log_factor)
         if regularization in ("Smoothness", "TV") and int(np.prod(self.mshape)) != self.M:
             raise ValueError("Smoothness/TV are defined on the full (nz, ny, nx) grid and cannot "
                              "be used with a topography-carved model")
         mw_d, apr_d = eng.vec(mw), eng.vec(mwapr)
-        eng.data_pass(mw_d)
+        eng.data_pass(mw_d, self._forward(mw_d))
         pm, grad = eng.vec(), eng.vec()
         eng.update(reg, mw_d, mw_d, apr_d, self.wmsq_dev, None, None, pm, None, None, grad, 0.0,
                    0.0, 0)
@@ -274,9 +272,7 @@ class GravMagModule:
         """dpre, data_value, data_gradient -- potential.py:688-717"""
         eng = self.engine()
         mw_d = eng.vec(mw)
-        if self.wavelet:
-            raise NotImplementedError("wavelet data_all: see gravmag.compressor*")
-        eng.data_pass(mw_d)
+        eng.data_pass(mw_d, self._forward(mw_d))
         sums = eng.sums.cpu().numpy()
         return eng.d.cpu().numpy(), float(sums[1]), 2.0 * eng.g[: self.M].cpu().numpy()
 

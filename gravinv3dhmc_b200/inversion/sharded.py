@@ -40,7 +40,7 @@ class _ShardState:
 
 def _grad_eval(st, chain, reg, x_in, mw_in, x_out, mw_out, grad_out, pcoef, dt, advance):
     eng = st.eng
-    eng.data_pass(mw_in)
+    eng.data_pass(mw_in, chain.model._forward(mw_in))
     eng.update(reg, x_in, mw_in, st.apr, chain.model.wmsq_dev, st.low, st.high, st.p, x_out, mw_out,
                grad_out, pcoef, dt, advance)
 

@@ -188,6 +188,13 @@ int gi_hmc_propose_philox(gi_hmc *h, uint64_t seed, uint64_t counter, double sig
 /* Benchmark / warm-up helper: run `nsteps` leapfrog steps (hmc.py:117-152) from the current state
  * without a Metropolis test; the momentum starts at p0_dev (device, length ld) or zero. */
 int gi_hmc_leapfrog_steps(gi_hmc *h, const double *p0_dev, int32_t nsteps, double dt);
+/* Wavelet-compressed forward (potential.py:693-696): d = Awcp @ DWT(mw) replaces Aw @ mw in every
+ * gradient evaluation of this handle; the gradient keeps the dense Aw^T (potential.py:708).
+ * kind 1 = compressor1D (nz,ny,nx ignored), 3 = compressor3D on the (nz,ny,nx) grid, 0 = off.
+ * The CSR arrays (N rows, ncoef columns) stay owned by the caller and must outlive the handle. */
+int gi_hmc_set_wavelet(gi_hmc *h, int32_t kind, int32_t nz, int32_t ny, int32_t nx,
+                       const int64_t *indptr_dev, const int32_t *indices_dev, const double *data_dev,
+                       int64_t ncoef);
 /* kernels launched by this handle since creation */
 int64_t gi_hmc_launch_count(const gi_hmc *h);
 void *gi_hmc_stream(const gi_hmc *h);
@@ -266,6 +273,14 @@ int gi_dwt_db4_l2_1d_batch(const double *x_dev, int64_t batch, int64_t x_bs, int
 int gi_dwt_db4_l2_3d_batch(const double *x_dev, int64_t batch, int64_t x_bs, int32_t nz, int32_t ny,
                            int32_t nx, double *out_dev, int64_t out_bs, int32_t out_shape[3],
                            void *stream);
+/* dense coefficient rows -> CSR (compressor*.kernelcompressor: entries with |c| < thr are zeroed,
+ * scipy's csr_matrix drops the zeros).  counts[row] = kept entries; after an exclusive scan into
+ * indptr (row offsets relative to this block of rows), gi_csr_fill writes indices/data in ascending
+ * column order. */
+int gi_csr_count(const double *dense_dev, int64_t nrows, int64_t ncols, int64_t row_stride, double thr,
+                 int64_t *counts_dev, void *stream);
+int gi_csr_fill(const double *dense_dev, int64_t nrows, int64_t ncols, int64_t row_stride, double thr,
+                const int64_t *indptr_dev, int32_t *indices_dev, double *data_dev, void *stream);
 /* y = A x for a CSR matrix (int64 indptr[nrows+1], int32 indices, f64 data) */
 int gi_csr_spmv(const int64_t *indptr_dev, const int32_t *indices_dev, const double *data_dev,
                 int64_t nrows, const double *x_dev, double *y_dev, void *stream);

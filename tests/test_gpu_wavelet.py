@@ -1,0 +1,149 @@
+"""GPU parity of the wavelet-compressed forward path (compressor1D/3D): db4 level-2 periodization
+DWT kernels, threshold -> CSR packing, CSR matvec and the sampler with `wavelet='1D'|'3D'`, against
+the CPU oracle's restatement of the PyWavelets conventions.
+
+PARITY UNPINNED upstream: PyWavelets is absent from this image and un-pinned by the reference
+(DESIGN.md section 5); what is checked here is CUDA == oracle restatement (1e-12) plus the
+size-independent properties any correct orthonormal transform has."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from gravinv3dhmc_b200 import _lib  # noqa: E402
+from gravinv3dhmc_b200.gravmag import compressor1D as cp1D, compressor3D as cp3D  # noqa: E402
+from gravinv3dhmc_b200.inversion import hmc, potential  # noqa: E402
+from oracle import oracle_np as onp  # noqa: E402
+
+
+def normwise(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("n", [8, 9, 37, 120, 6000, 6001])
+def test_dwt_1d_vs_oracle(n):
+    rng = np.random.RandomState(n)
+    x = rng.standard_normal(n)
+    ref = onp.coeffs_to_array_1d(onp.wavedec_1d(x))
+    assert cp1D.ncoef(n) == ref.size
+    xd = torch.as_tensor(x).cuda()
+    out = torch.full((ref.size,), np.nan, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().gi_dwt_db4_l2_1d(_lib.ptr(xd), n, _lib.ptr(out), None, _lib.stream_ptr()))
+    assert normwise(out.cpu().numpy(), ref) < 1e-13
+    if n % 4 == 0:  # orthonormal when the lengths nest: energy is preserved
+        assert abs(np.sum(out.cpu().numpy() ** 2) - np.sum(x ** 2)) < 1e-10 * np.sum(x ** 2)
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 4), (5, 6, 4), (10, 30, 20), (5, 7, 9), (1, 8, 8), (3, 2, 17)])
+def test_dwt_3d_vs_oracle(shape):
+    rng = np.random.RandomState(sum(shape))
+    x = rng.standard_normal(shape)
+    ref = onp.coeffs_to_array_3d(onp.wavedecn_3d(x))
+    assert cp3D.coeff_shape(shape) == ref.shape
+    xd = torch.as_tensor(x.ravel()).cuda()
+    out = torch.full((ref.size,), np.nan, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().gi_dwt_db4_l2_3d(_lib.ptr(xd), *shape, _lib.ptr(out), None,
+                                           _lib.stream_ptr()))
+    assert normwise(out.cpu().numpy().reshape(ref.shape), ref) < 1e-13
+    if shape == (10, 30, 20):
+        assert ref.shape == (11, 31, 20)  # non-nesting shapes pad with zeros
+
+
+def small_model(g, wavelet):
+    o = g["small_obs"]
+    return potential.GravMagModule(g["small_dobs"], (0, 400, 0, 600, 0, 500), (100, 100, 100),
+                                   (o[:, 0], o[:, 1], o[:, 2]), verbose=False, wavelet=wavelet)
+
+
+@pytest.mark.parametrize("kind", ["1D", "3D"])
+def test_kernelcompressor_and_forward_vs_oracle(golden, kind):
+    g = golden["potential_hmc"]
+    Aw, mshape = g["small_Aw"], tuple(g["small_mshape"])
+    model = small_model(g, kind)
+    ref = onp.kernelcompressor_1d(Aw) if kind == "1D" else onp.kernelcompressor_3d(Aw, mshape)
+    got = model.Awcp.toscipy()
+    assert got.shape == ref.shape
+    # bookkeeping bit-exact: same sparsity pattern (no coefficient sits within 1e-12 of the threshold)
+    assert np.array_equal(got.indptr, ref.indptr) and np.array_equal(got.indices, ref.indices)
+    assert normwise(got.data, ref.data) < 1e-12
+    assert 0 < got.nnz < ref.shape[0] * ref.shape[1]
+    rng = np.random.RandomState(3)
+    m = rng.uniform(0, 0.3, Aw.shape[1])
+    if kind == "1D":
+        d, dref = cp1D.modelcompressor(m, model.Awcp), onp.modelcompressor_1d(m, ref)
+    else:
+        d, dref = cp3D.modelcompressor(m, model.Awcp, mshape), onp.modelcompressor_3d(m, ref, mshape)
+    assert normwise(d, dref) < 1e-12
+    assert normwise(model.Awcp @ np.ones(ref.shape[1]), ref @ np.ones(ref.shape[1])) < 1e-12
+    # the compressed forward approximates the dense one (threshold 1e-3 on unit-norm columns) when
+    # the lengths nest (120 -> 60 -> 30); on the odd-length (5, 6, 4) grid the 'periodization'
+    # extension duplicates a sample, the transform is no longer orthonormal and the compressed
+    # product is NOT close to the dense one -- in the reference as well (its (10, 30, 20) example
+    # grid has odd lengths at level 2).
+    if kind == "1D":
+        assert normwise(d, Aw @ m) < 0.05
+    # misfit_and_grad: compressed forward, dense gradient (potential.py:693-708)
+    om = onp.OracleModel(Aw, g["small_wm"], g["small_dobs"], mshape, wavelet=kind)
+    for reg in ("Damping", "MS"):
+        got_mg = model.misfit_and_grad(g["mg_x"], g["mg_x0"], None, None, "mandatory", 1000, 0.7,
+                                       regulization=reg, beta=0.001)
+        ref_mg = om.misfit_and_grad(g["mg_x"], g["mg_x0"], None, None, "mandatory", 1000, 0.7,
+                                    regulization=reg, beta=0.001)
+        assert np.allclose([got_mg[0], got_mg[3], got_mg[4]], [ref_mg[0], ref_mg[3], ref_mg[4]],
+                           rtol=1e-10)
+        assert normwise(got_mg[1], ref_mg[1]) < 1e-10 and normwise(got_mg[2], ref_mg[2]) < 1e-10
+
+
+def test_threshold_zero_is_the_dense_product():
+    """orthonormality (even, nesting dims): with thr = 0, Awcp @ DWT(m) == Aw @ m"""
+    rng = np.random.RandomState(11)
+    shape = (4, 8, 8)
+    M = int(np.prod(shape))
+    A = rng.standard_normal((19, M))
+    m = rng.standard_normal(M)
+    Ad = torch.as_tensor(A).cuda()
+    c3 = cp3D.kernelcompressor(Ad, shape, thr=0.0)
+    c1 = cp1D.kernelcompressor(Ad, thr=0.0)
+    assert normwise(cp3D.modelcompressor(m, c3, shape), A @ m) < 1e-11
+    assert normwise(cp1D.modelcompressor(m, c1), A @ m) < 1e-11
+    with pytest.raises(ValueError, match="reshape"):
+        cp3D.kernelcompressor(Ad, (4, 8, 9))
+
+
+@pytest.mark.parametrize("kind", ["1D", "3D"])
+def test_wavelet_chain_matches_oracle(golden, kind, tmp_path):
+    g = golden["potential_hmc"]
+    model = small_model(g, kind)
+    M, dobs = model.M, g["small_dobs"]
+    om = onp.OracleModel(g["small_Aw"], g["small_wm"], dobs, tuple(g["small_mshape"]), wavelet=kind)
+    b = np.ones((M, 2))
+    b[:, 0], b[:, 1] = 0.0, 0.3
+    args = (0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b, "mandatory", 1000)
+    traces = []
+    real = hmc.HamitonianMC._leapfrog
+
+    def patched(self, xcur, dt, L, alpha, fignum=0, trace=None):
+        tr = {}
+        out = real(self, xcur, dt, L, alpha, fignum, trace=tr)
+        traces.append(tr)
+        return out
+
+    hmc.HamitonianMC._leapfrog = patched
+    try:
+        ch = hmc.HMCSample(model, 6, 0, *args, dobs, "Fixed", 0.8, 0.5, "MS", 0.001, 100, 0.05,
+                           save_folder=str(tmp_path / "w"), quiet=True)
+    finally:
+        hmc.HamitonianMC._leapfrog = real
+    otr = []
+    ref = onp.hmc_sample(om, 6, 0, *args, 0.5, "MS", 0.001, 100, 0.05, trace=otr)
+    assert [(L, bool(a)) for L, a in ch.proposals] == [(L, bool(a)) for L, a in ref["log"]]
+    for t, o in zip(traces, otr):
+        rx = np.array([x for x, _ in o["steps"]])
+        rU = np.array([U for _, U in o["steps"]])
+        assert np.max(np.abs(t["x"] - rx) / np.max(np.abs(rx), axis=1, keepdims=True)) < 1e-9
+        assert np.max(np.abs(t["U"] - rU) / np.abs(rU)) < 1e-9
+    mis = np.loadtxt(tmp_path / "w0" / "misfit.dat", ndmin=2)
+    assert np.allclose(mis, ref["misfit"], rtol=0, atol=2e-8)
