@@ -167,6 +167,13 @@ def stream_ptr(torch=None):
     return C.c_void_p(_t.cuda.current_stream().cuda_stream)
 
 
+def sync():
+    """wait for the current CUDA stream"""
+    import torch as _t
+
+    _t.cuda.current_stream().synchronize()
+
+
 def padded_ld(M: int) -> int:
     """leading dimension: M rounded up to 32 doubles (256 B) so every row starts sector-aligned"""
     return ((int(M) + 31) // 32) * 32

@@ -65,7 +65,7 @@ def matvec_padded(Gpad, M, vec, torch):
     try:
         _lib.check(L.gi_gemv_fwd(plan, _lib.ptr(Gpad), _lib.ptr(x), _lib.ptr(d), _lib.stream_ptr()),
                    "gi_gemv_fwd")
-        torch.cuda.current_stream().synchronize()
+        _lib.sync()
     finally:
         L.gi_plan_destroy(plan)
     return d

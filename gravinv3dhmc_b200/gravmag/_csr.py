@@ -79,7 +79,7 @@ def rows_to_csr(Aw, transform, ncoef, thr):
         _lib.check(L.gi_csr_fill(_lib.ptr(dense), nb, ncoef, ncoef, float(thr),
                                  C.c_void_p(indptr.data_ptr() + 8 * r0), _lib.ptr(indices),
                                  _lib.ptr(data), s), "gi_csr_fill")
-    torch.cuda.current_stream().synchronize()
+    _lib.sync()
     return DeviceCSR((N, ncoef), indptr, indices, data)
 
 

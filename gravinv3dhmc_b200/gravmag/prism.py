@@ -41,7 +41,7 @@ def assemble(xp, yp, zp, table, rows=None, device=None):
     _lib.check(L.gi_prism_gz_assemble(_lib.ptr(x_d), _lib.ptr(y_d), _lib.ptr(z_d), n,
                                       _lib.ptr(tab_d), M, G * SI2MGAL, _lib.ptr(Gd), ld,
                                       _lib.stream_ptr()), "gi_prism_gz_assemble")
-    torch.cuda.current_stream().synchronize()
+    _lib.sync()
     return Gd, M
 
 

@@ -175,7 +175,7 @@ class GravMagModule:
             raise ValueError("sensitivity weighting: the last column of the kernel is all zero")
         _lib.check(L.gi_scale_columns(_lib.ptr(A), n, self.M, ld, _lib.ptr(wminv), s),
                    "gi_scale_columns")
-        torch.cuda.current_stream().synchronize()
+        _lib.sync()
         self.wm_dev, self.wminv_dev, self.wmsq_dev = wm, wminv, wmsq
         self.Aw = A[:, : self.M]
         row = np.arange(0, self.M)

@@ -40,17 +40,22 @@ def main():
     om = onp.OracleModel(g["small_Aw"], g["small_wm"], dobs, tuple(g["small_mshape"]))
     b = np.ones((M, 2))
     b[:, 0], b[:, 1] = -5.0, 5.0
+    b_tv = np.ones((M, 2))
+    b_tv[:, 0], b_tv[:, 1] = 0.0, 0.3
     tmp = tempfile.mkdtemp()
     # ---- single chain, row-sharded ----
-    for reg in ("Damping", "TV"):
-        ch = hmc.HMCSample(model, 4, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
-                           "mandatory", 1000, dobs, "Fixed", 0.8, 1.0, reg, 0.001, 3, 1.0, myrank=0,
-                           save_folder=os.path.join(tmp, "s_%s_%d_" % (reg, rank)), quiet=True)
-        ref = onp.hmc_sample(om, 4, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
-                             "mandatory", 1000, 1.0, reg, 0.001, 3, 1.0)
+    cases = {"Damping": (1.0, 0.1, 1.0, [4, 9], b),           # frequent rejections
+             "TV": (0.05, 0.02, 0.05, [3, 8], b_tv)}             # the golden TV chain's parameters
+    for reg, (alpha, delta, Sigma, Lr, bb) in cases.items():
+        ch = hmc.HMCSample(model, 4, 0, delta, Lr, np.ones(M) * 0.001, np.ones(M) * 0.001, bb,
+                           "mandatory", 1000, dobs, "Fixed", 0.8, alpha, reg, 0.001, 3, Sigma, myrank=0,
+                           save_folder=os.path.join(tmp, "s_%s_r%d_" % (reg, rank)), quiet=True,
+                           max_proposals=30)
+        ref = onp.hmc_sample(om, 4, 0, delta, Lr, np.ones(M) * 0.001, np.ones(M) * 0.001, bb,
+                             "mandatory", 1000, alpha, reg, 0.001, 3, Sigma, max_proposals=30)
         assert [(L, bool(a)) for L, a in ch.proposals] == [(L, bool(a)) for L, a in ref["log"]], reg
-        scale = np.max(np.abs(ref["x"]))
-        assert np.max(np.abs(ch.x_final - ref["x"])) < 1e-9 * scale, reg
+        assert np.max(np.abs(ch.x_final - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"])), reg
+        assert any(a for _, a in ch.proposals), reg
     # ---- batch of chains, row-sharded ----
     nch, nprops = 5, 5
     bt = batched.HMCBatch(model, nch, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
