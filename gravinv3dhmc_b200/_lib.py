@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "_build", "libgravinv_b200.so")
+# GRAVINV_B200_LIB points at an alternative build of the same ABI (kernel tuning experiments)
+SO_PATH = os.environ.get("GRAVINV_B200_LIB") or os.path.join(HERE, "_build", "libgravinv_b200.so")
 
 GI_OK, GI_ERR_INVALID, GI_ERR_CUDA, GI_ERR_OVERFLOW, GI_ERR_NOMEM = 0, -1, -2, -3, -4
 REG_KINDS = {"Damping": 0, "MS": 1, "Smoothness": 2, "TV": 3}

@@ -19,18 +19,19 @@ def stale() -> bool:
     return any(os.path.getmtime(f) > t for f in SRC + HDR if os.path.exists(f))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
+    if not force and not stale() and out == OUT:
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include")]
+    cmd += os.environ.get("GI_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [s for s in SRC if os.path.exists(s)] + ["-o", OUT]
+    cmd += [s for s in SRC if os.path.exists(s)] + ["-o", out]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

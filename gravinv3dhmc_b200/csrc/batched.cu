@@ -60,11 +60,20 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 }
 
 constexpr int kGemmThreads = 256;
-constexpr int kStages = 4;
+#ifndef GI_STAGES
+#define GI_STAGES 4
+#endif
+#ifndef GI_FWDK
+#define GI_FWDK 32
+#endif
+#ifndef GI_ADJK
+#define GI_ADJK 16
+#endif
+constexpr int kStages = GI_STAGES;
 constexpr int kFwdRows = 128;  // rows per CTA
-constexpr int kFwdK = 32;      // voxels per stage
+constexpr int kFwdK = GI_FWDK;  // voxels per stage (32 or 64)
 constexpr int kAdjCols = 256;  // voxels per CTA
-constexpr int kAdjK = 16;      // rows per stage
+constexpr int kAdjK = GI_ADJK;  // rows per stage (16 or 32)
 
 template <int NT>
 __host__ __device__ constexpr int fwd_stage_bytes() { return kFwdRows * kFwdK * 8 + 8 * NT * kFwdK * 8; }
@@ -74,77 +83,85 @@ __host__ __device__ constexpr int adj_stage_bytes() { return kAdjK * kAdjCols * 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// WC = warps along the chain dimension: the CTA has 8*WC warps, warp (wr, wc) owns rows
+// 16*wr..16*wr+15 and the n-tiles wc*NT/WC .. (wc+1)*NT/WC-1.  WC = 2 doubles the warps per
+// scheduler (4 instead of 2), which hides the DMMA issue latency (ncu: stall_wait 39 % at WC = 1).
+template <int NT, int WC>
+__global__ void __launch_bounds__(kGemmThreads * WC, 1)
 gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ X, int64_t nrows,
                 int64_t kchunk, int64_t rowblocks, double *__restrict__ part) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int T = kGemmThreads * WC;
     constexpr int C = 8 * NT;
+    constexpr int NTW = NT / WC;
     constexpr int GB = kFwdRows * kFwdK * 8;
     constexpr int STAGE = fwd_stage_bytes<NT>();
+    constexpr int CPR = kFwdK / 2;          // 16-B chunks per tile row
+    constexpr int PITCH = kFwdK * 8;        // bytes per tile row
+    constexpr int RPP = T / CPR;            // tile rows covered by one pass of the CTA's threads
+    constexpr int GU = kFwdRows / RPP;      // Aw chunks per thread per stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int wr = warp & 7, wc = warp >> 3;
     const int64_t tile = blockIdx.x;
     const int64_t kc = tile / rowblocks, rb = tile - kc * rowblocks;
     const int64_t r0 = rb * kFwdRows;
     const int64_t c0 = kc * kchunk, c1 = min(c0 + kchunk, ld);
     const int ntiles = (int)((c1 - c0) / kFwdK);
 
-    // this thread's copy slots: Aw rows (tid>>4) + 16u, 16-B chunk tid&15 (swizzled by row parity)
-    const int lrow = tid >> 4, lch = tid & 15;
-    const double *gsrc[8];
+    // this thread's copy slots: Aw rows tid/CPR + RPP*u, 16-B chunk tid%CPR (swizzled by row parity)
+    const int lrow = tid / CPR, lch = tid % CPR;
+    const double *gsrc[GU];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-        gsrc[u] = G + min(r0 + lrow + 16 * u, nrows - 1) * ld + c0 + 2 * lch;
-    const int gdst = lrow * 256 + ((lch ^ ((lrow & 1) << 2)) << 4);  // + 16u rows: parity unchanged
+    for (int u = 0; u < GU; ++u)
+        gsrc[u] = G + min(r0 + lrow + RPP * u, nrows - 1) * ld + c0 + 2 * lch;
+    const int gdst = lrow * PITCH + ((lch ^ ((lrow & 1) << 2)) << 4);  // + RPP*u rows: parity unchanged
+
+    constexpr int XU = (C + RPP - 1) / RPP;  // X chunks per thread per stage
+    const double *xsrc = X + (int64_t)lrow * ld + c0 + 2 * lch;  // chain lrow; + RPP*u chains
+    const int xdst = GB + gdst;
 
     auto load_stage = [&](int s, int kt) {
         unsigned char *base = smem + s * STAGE;
         const int64_t koff = (int64_t)kt * kFwdK;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) cp_async16(base + gdst + u * 16 * 256, gsrc[u] + koff);
+        for (int u = 0; u < GU; ++u) cp_async16(base + gdst + u * RPP * PITCH, gsrc[u] + koff);
 #pragma unroll
-        for (int u = 0; u < (C * 16 + kGemmThreads - 1) / kGemmThreads; ++u) {
-            const int id = tid + kGemmThreads * u;
-            if (C * 16 % kGemmThreads == 0 || id < C * 16) {
-                const int row = id >> 4;
-                cp_async16(base + GB + row * 256 + ((lch ^ ((row & 1) << 2)) << 4),
-                           X + (int64_t)row * ld + c0 + koff + 2 * lch);
-            }
+        for (int u = 0; u < XU; ++u) {
+            if (C % RPP == 0 || lrow + RPP * u < C)
+                cp_async16(base + xdst + u * RPP * PITCH, xsrc + (int64_t)u * RPP * ld + koff);
         }
     };
 
-    double acc[2][NT][2];
+    double acc[2][NTW][2];
 #pragma unroll
     for (int rm = 0; rm < 2; ++rm)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) acc[rm][j][0] = acc[rm][j][1] = 0.0;
+        for (int j = 0; j < NTW; ++j) acc[rm][j][0] = acc[rm][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
         if (s < ntiles) load_stage(s, s);
         cp_async_commit();
     }
-    const int sw = (g & 1) << 2;  // rows 16w + 8rm + g and chains 8j + g have the parity of g
+    const int sw = (g & 1) << 2;  // rows 16wr + 8rm + g and chains 8j + g have the parity of g
     for (int kt = 0; kt < ntiles; ++kt) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
-        if (kt + kStages - 1 < ntiles) load_stage((kt + kStages - 1) % kStages, kt + kStages - 1);
-        cp_async_commit();
         const unsigned char *gs = smem + (kt % kStages) * STAGE;
-        const unsigned char *xs = gs + GB;
+        const unsigned char *xs = gs + GB + wc * NTW * 8 * PITCH;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < kFwdK / 16; ++q) {
             const int ch_lo = ((8 * q + t) ^ sw) << 4, ch_hi = ((8 * q + 4 + t) ^ sw) << 4;
             double a[2][4];
 #pragma unroll
             for (int rm = 0; rm < 2; ++rm) {
-                const unsigned char *rowp = gs + (warp * 16 + rm * 8 + g) * 256;
+                const unsigned char *rowp = gs + (wr * 16 + rm * 8 + g) * PITCH;
                 lds128(rowp + ch_lo, a[rm][0], a[rm][1]);
                 lds128(rowp + ch_hi, a[rm][2], a[rm][3]);
             }
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const unsigned char *rowp = xs + (8 * j + g) * 256;
+            for (int j = 0; j < NTW; ++j) {
+                const unsigned char *rowp = xs + (8 * j + g) * PITCH;
                 double b[4];
                 lds128(rowp + ch_lo, b[0], b[1]);
                 lds128(rowp + ch_hi, b[2], b[3]);
@@ -154,16 +171,22 @@ gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
                     dmma884(acc[1][j][0], acc[1][j][1], a[1][i], b[i]);
                 }
             }
+            if (q == 0) {
+                // refill the stage consumed in the previous iteration; issued behind the first
+                // k-group so the tensor pipe has work while the copies are set up
+                if (kt + kStages - 1 < ntiles) load_stage((kt + kStages - 1) % kStages, kt + kStages - 1);
+                cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();
 #pragma unroll
     for (int rm = 0; rm < 2; ++rm) {
-        const int64_t row = r0 + warp * 16 + rm * 8 + g;
+        const int64_t row = r0 + wr * 16 + rm * 8 + g;
         if (row < nrows) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int64_t chain = 8 * j + 2 * t;
+            for (int j = 0; j < NTW; ++j) {
+                const int64_t chain = 8 * (wc * NTW + j) + 2 * t;
                 part[(kc * C + chain) * nrows + row] = acc[rm][j][0];
                 part[(kc * C + chain + 1) * nrows + row] = acc[rm][j][1];
             }
@@ -174,85 +197,114 @@ gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
 // ---------------------------------------------------------------------------------------------
 // adjoint
 // ---------------------------------------------------------------------------------------------
-template <int NT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int NT, int WC>
+__global__ void __launch_bounds__(kGemmThreads * WC, 1)
 gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ R, int64_t npad,
                 int64_t nrows, double *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int T = kGemmThreads * WC;
     constexpr int C = 8 * NT;
+    constexpr int NTW = NT / WC;
     constexpr int GB = kAdjK * kAdjCols * 8;
     constexpr int STAGE = adj_stage_bytes<NT>();
+    constexpr int GU = kAdjK * 128 / T;  // Aw chunks per thread per stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int wv = warp & 7, wc = warp >> 3;  // voxel group, chain half
     const int64_t v0 = (int64_t)blockIdx.x * kAdjCols;
     const int ntiles = (int)(npad / kAdjK);
 
-    // copy slots: Aw rows (tid>>7) + 2u of the stage, 16-B chunk tid&127 of the 256-voxel strip
+    // copy slots: Aw rows (tid>>7) + (T/128)u of the stage, 16-B chunk tid&127 of the 256-voxel strip.
+    // All addressing is hoisted: per stage a thread only bumps one pointer by 16 rows (the row
+    // clamp is needed in the last, partial stage only), so the per-stage integer work that every
+    // warp executes right after the barrier -- while no DMMA is in flight -- stays minimal.
     const int lrow = tid >> 7, lcv = tid & 127;
     const int64_t col = (v0 + 2 * lcv < ld) ? v0 + 2 * lcv : 0;  // strip tail: any valid address
-    const int rchain = tid >> 3, rec = tid & 7;
+    constexpr int RCP = kAdjK / 2;     // 16-B chunks per R tile row
+    constexpr int RPITCH = kAdjK * 8;  // bytes per R tile row
+    constexpr int RCH = T / RCP;       // chains covered by one pass of the CTA's threads
+    const int rchain = tid / RCP, rec = tid % RCP;
+    const int full_tiles = (int)(nrows / kAdjK);  // stages whose 16 rows all exist
+    const double *gp = G + (int64_t)lrow * ld + col;  // row lrow of stage 0; + (T/128)u rows; + 16 rows per stage
+    const int64_t gstep = (int64_t)(T / 128) * ld;
+    int gdst[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+        const int row = lrow + (T / 128) * u;
+        gdst[u] = row * 2048 + ((lcv ^ (2 * (row & 3))) << 4);
+    }
+    const double *rp = R + (int64_t)rchain * npad + 2 * rec;
+    const int rdst = GB + rchain * RPITCH + ((rec ^ (2 * (rchain & 3))) << 4);
 
     auto load_stage = [&](int s, int ot) {
         unsigned char *base = smem + s * STAGE;
-        const int64_t o0 = (int64_t)ot * kAdjK;
+        const double *src = gp + (int64_t)ot * kAdjK * ld;
+        if (ot < full_tiles) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int row = lrow + 2 * u;
-            cp_async16(base + row * 2048 + ((lcv ^ (2 * (row & 3))) << 4),
-                       G + min(o0 + row, nrows - 1) * ld + col);
+            for (int u = 0; u < GU; ++u) cp_async16(base + gdst[u], src + u * gstep);
+        } else {
+            const int64_t o0 = (int64_t)ot * kAdjK;
+#pragma unroll
+            for (int u = 0; u < GU; ++u)
+                cp_async16(base + gdst[u],
+                           G + min(o0 + lrow + (T / 128) * u, nrows - 1) * ld + col);
         }
 #pragma unroll
-        for (int u = 0; u < (C * 8 + kGemmThreads - 1) / kGemmThreads; ++u) {
-            const int chain = rchain + 32 * u;
-            if (C * 8 % kGemmThreads == 0 || chain < C)
-                cp_async16(base + GB + chain * 128 + ((rec ^ (2 * (chain & 3))) << 4),
-                           R + (int64_t)chain * npad + o0 + 2 * rec);
+        for (int u = 0; u < (C + RCH - 1) / RCH; ++u) {
+            if (C % RCH == 0 || rchain + RCH * u < C)
+                cp_async16(base + rdst + u * RCH * RPITCH,  // chain & 3 unchanged by + RCH
+                           rp + (int64_t)u * RCH * npad + (int64_t)ot * kAdjK);
         }
     };
 
-    double acc[4][NT][2];
+    double acc[4][NTW][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
         if (s < ntiles) load_stage(s, s);
         cp_async_commit();
     }
-    const int a_lo = ((16 * warp + g) ^ (2 * t)) << 4, a_hi = ((16 * warp + 8 + g) ^ (2 * t)) << 4;
+    const int a_lo = ((16 * wv + g) ^ (2 * t)) << 4, a_hi = ((16 * wv + 8 + g) ^ (2 * t)) << 4;
     for (int ot = 0; ot < ntiles; ++ot) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
-        if (ot + kStages - 1 < ntiles) load_stage((ot + kStages - 1) % kStages, ot + kStages - 1);
-        cp_async_commit();
         const unsigned char *gs = smem + (ot % kStages) * STAGE;
-        const unsigned char *rs = gs + GB;
+        const unsigned char *rs = gs + GB + wc * NTW * 8 * RPITCH;
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {
+        for (int kq = 0; kq < kAdjK / 4; ++kq) {
             const unsigned char *rowp = gs + (4 * kq + t) * 2048;
             double a[4];
-            lds128(rowp + a_lo, a[0], a[1]);  // voxels 32w + 2g + {0,1}
-            lds128(rowp + a_hi, a[2], a[3]);  // voxels 32w + 16 + 2g + {0,1}
+            lds128(rowp + a_lo, a[0], a[1]);  // voxels 32wv + 2g + {0,1}
+            lds128(rowp + a_hi, a[2], a[3]);  // voxels 32wv + 16 + 2g + {0,1}
             const int e = ((4 * kq + t) ^ (4 * (g & 3))) << 3;
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const double b = lds64(rs + (8 * j + g) * 128 + e);
+            for (int j = 0; j < NTW; ++j) {
+                const double b = lds64(rs + (8 * j + g) * RPITCH + e);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
+            }
+            if (kq == 0) {
+                // refill the stage consumed in the previous iteration (every warp is past the
+                // barrier above, so nobody reads it any more); issued here, behind the first
+                // k-group, so that the tensor pipe already has work while the copies are set up
+                if (ot + kStages - 1 < ntiles) load_stage((ot + kStages - 1) % kStages, ot + kStages - 1);
+                cp_async_commit();
             }
         }
     }
     cp_async_wait<0>();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int64_t v = v0 + 32 * warp + 16 * h + 2 * g;
+        const int64_t v = v0 + 32 * wv + 16 * h + 2 * g;
         if (v < ld) {
 #pragma unroll
-            for (int j = 0; j < NT; ++j)
+            for (int j = 0; j < NTW; ++j)
 #pragma unroll
                 for (int e2 = 0; e2 < 2; ++e2) {
-                    double *dst = out + (int64_t)(8 * j + 2 * t + e2) * ld + v;
+                    double *dst = out + (int64_t)(8 * (wc * NTW + j) + 2 * t + e2) * ld + v;
                     asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst), "d"(acc[2 * h][j][e2]),
                                  "d"(acc[2 * h + 1][j][e2])
                                  : "memory");
@@ -438,11 +490,16 @@ using namespace gi;
 // =============================================================================================
 static int pick_nt(int nchains) { return nchains <= 8 ? 1 : nchains <= 16 ? 2 : nchains <= 32 ? 4 : 8; }
 
+// warps along the chain dimension per n-tile count (see gemm_fwd_kernel)
+template <int NT> struct WarpSplit { static constexpr int fwd = NT >= 4 ? 2 : 1, adj = NT >= 4 ? 2 : 1; };
+
 template <int NT>
 static int set_smem_attrs() {
-    GI_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GI_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<NT, WarpSplit<NT>::fwd>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kStages * fwd_stage_bytes<NT>()));
-    GI_CUDA(cudaFuncSetAttribute(gemm_adj_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GI_CUDA(cudaFuncSetAttribute(gemm_adj_kernel<NT, WarpSplit<NT>::adj>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kStages * adj_stage_bytes<NT>()));
     return GI_OK;
 }
@@ -489,7 +546,8 @@ void gi::batched_plan_free(gi_plan *p) {
 int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s) {
     const unsigned grid = (unsigned)(p->b_nkc * p->b_rowblocks);
 #define GI_FWD(NT)                                                                             \
-    gemm_fwd_kernel<NT><<<grid, kGemmThreads, kStages * fwd_stage_bytes<NT>(), s>>>(           \
+    gemm_fwd_kernel<NT, WarpSplit<NT>::fwd>                                                    \
+        <<<grid, kGemmThreads * WarpSplit<NT>::fwd, kStages * fwd_stage_bytes<NT>(), s>>>(     \
         G, p->ld, X, p->nrows, p->b_kchunk, p->b_rowblocks, p->b_part)
     switch (p->b_nt) {
         case 1: GI_FWD(1); break;
@@ -505,7 +563,8 @@ int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream
 int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s) {
     const unsigned grid = (unsigned)p->b_strips;
 #define GI_ADJ(NT)                                                                             \
-    gemm_adj_kernel<NT><<<grid, kGemmThreads, kStages * adj_stage_bytes<NT>(), s>>>(           \
+    gemm_adj_kernel<NT, WarpSplit<NT>::adj>                                                    \
+        <<<grid, kGemmThreads * WarpSplit<NT>::adj, kStages * adj_stage_bytes<NT>(), s>>>(     \
         G, p->ld, R, p->b_npad, p->nrows, out)
     switch (p->b_nt) {
         case 1: GI_ADJ(1); break;
