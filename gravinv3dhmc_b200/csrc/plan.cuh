@@ -49,6 +49,7 @@ struct UpdateArgs {
     unsigned int *counter;  // last-block ticket
     double *sums;           // [2] = Um, [3] = K after update, [4] = K before update
     int save_k0;            // also park K before the update in sums[5] (opening half step)
+    const double *p_in;     // momentum is read from here (written to p) when non-null
 };
 
 int check_reg(const gi_reg_params *reg, int64_t M);
@@ -138,7 +139,7 @@ __device__ __forceinline__ void update_body(const UpdateArgs &a, bool copy_x) {
             grad = gd + a.reg.alpha * gm;  // potential.py:843
         }
         if (a.grad_out) a.grad_out[j] = grad;
-        double p = a.p[j];
+        double p = a.p_in ? a.p_in[j] : a.p[j];
         k_before = p * p;
         p = __dsub_rn(p, __dmul_rn(a.pcoef, grad));  // hmc.py:114,150,152
         if (a.advance) {

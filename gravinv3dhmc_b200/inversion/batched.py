@@ -11,9 +11,11 @@ has `ndraws + nsamples` accepted proposals (hmc.py:295).
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 import sys
+import threading
 
 import numpy as np
 
@@ -134,6 +136,70 @@ class _ShardedBatchState:
             self.d_cur[idx] = eng.d[idx]
 
 
+class _DrawAhead:
+    """Prepares the draws of upcoming proposals -- (L, p0 = randn(M)*Sigma, u) per chain, consumed
+    from `RandomState(seed + c)` in the reference's order (hmc.py:297,95,165) -- on background
+    threads while the GPU runs (numpy's generators and the ctypes calls both release the GIL).
+    Chain c is served by worker c % nworkers, so every chain's stream is consumed sequentially."""
+
+    def __init__(self, streams, Lrange, M, Sigma, depth=2, nworkers=None):
+        self.streams, self.Lrange, self.M, self.Sigma, self.depth = streams, Lrange, M, Sigma, depth
+        self.ready = [collections.deque() for _ in streams]
+        self.enabled = [True] * len(streams)
+        self.cv = threading.Condition()
+        self.stop_flag = False
+        n = nworkers or max(1, min(8, (os.cpu_count() or 2) // 2, len(streams)))
+        self.workers = [threading.Thread(target=self._run, args=(k, n), daemon=True) for k in range(n)]
+
+    def start(self):
+        for w in self.workers:
+            w.start()
+
+    def _todo(self, k, n):
+        return [c for c in range(k, len(self.streams), n)
+                if self.enabled[c] and len(self.ready[c]) < self.depth]
+
+    def _run(self, k, n):
+        while True:
+            with self.cv:
+                while not self.stop_flag and not self._todo(k, n):
+                    self.cv.wait(0.05)
+                if self.stop_flag:
+                    return
+                todo = self._todo(k, n)
+            for c in todo:
+                rs = self.streams[c]
+                L = int(rs.randint(self.Lrange[0], self.Lrange[1] + 1))
+                p0 = rs.randn(self.M) * self.Sigma
+                u = float(rs.rand())
+                with self.cv:
+                    self.ready[c].append((L, p0, u))
+                    self.cv.notify_all()
+
+    def wait_primed(self):
+        with self.cv:
+            while any(self.enabled[c] and len(self.ready[c]) < self.depth
+                      for c in range(len(self.streams))):
+                self.cv.wait(0.05)
+
+    def take(self, c):
+        with self.cv:
+            while not self.ready[c]:
+                self.cv.wait(0.05)
+            d = self.ready[c].popleft()
+            self.cv.notify_all()
+        return d
+
+    def disable(self, c):
+        with self.cv:
+            self.enabled[c] = False
+
+    def stop(self):
+        with self.cv:
+            self.stop_flag = True
+            self.cv.notify_all()
+
+
 class HMCBatch:
     def __init__(self, model, nchains, delta, Lrange, initial_model, aprior_model, boundaries,
                  constraint, log_factor, dobs, RegulFactor, regularization, beta, seed, Sigma,
@@ -168,6 +234,7 @@ class HMCBatch:
         self._philox_counter = 0
         self._h = None
         self._sh = None
+        self._ahead = None
         _lib.require_cuda()
         mw = self.initial_model
         if constraint == "logarithmic":     # hmc.py:271-273
@@ -270,6 +337,115 @@ class HMCBatch:
                            "gi_hmcb_get_state")
         return out
 
+    def start_draws(self, wait=False):
+        """start preparing the draws of the next proposals on background threads (optional; `stream`
+        does it itself).  `wait=True` returns once two proposals per chain are ready."""
+        self._ahead = _DrawAhead(self.streams, self.Lrange, self.model.M, self.Sigma)
+        self._ahead.start()
+        self._stream_buffers()
+        if wait:
+            self._ahead.wait_primed()
+        return self._ahead
+
+    def _stream_buffers(self):
+        """record array + pinned staging for the positions that come back with every record"""
+        if getattr(self, "_recs", None) is None:
+            torch = _lib.require_cuda()
+            cap = max(2 * self.nchains, 64)
+            self._recs = (_lib.StreamRecord * cap)()
+            self._xh = torch.empty((cap, self.model.M), dtype=torch.float64).pin_memory()
+        return self._recs, self._xh
+
+    def stream(self, nsamples, ndraws, max_proposals=None, write=True, on_record=None):
+        """hmc.py:252-343 for every chain, streaming: each chain runs its proposals back to back and
+        a chain that ends a trajectory opens the next one in the same batch step (`gi_hmcb_stream_*`),
+        so no chain idles while others finish longer trajectories.  Same draws, same decisions and
+        same files as `sample()`; single-GPU only."""
+        if self._sh is not None:
+            raise NotImplementedError("streaming is a single-GPU mode; use sample() when row-sharded")
+        if self.rng != "numpy":
+            raise NotImplementedError("streaming uses the host (reference-order) RNG")
+        torch = _lib.require_cuda()
+        lib = _lib.lib()
+        nc, M = self.nchains, self.model.M
+        folders = [self.save_folder + str(c) for c in range(nc)]
+        if write:
+            for fo in folders:
+                if not os.path.exists(fo):
+                    os.mkdir(fo)
+                if os.path.exists(fo + "/model.dat"):
+                    os.remove(fo + "/model.dat")
+        data_size, model_size = self.dobs.shape[0], self.initial_model.shape[0]
+        alpha, target = self.RegulFactor, ndraws + nsamples
+        recs, xh = self._stream_buffers()
+        cap = len(recs)
+        nrec, ndone = C.c_int32(), C.c_int32()
+        count, fed, inflight = [0] * nc, [0] * nc, [0] * nc
+        live = [True] * nc           # still needs accepted samples
+        ahead = self._ahead or self.start_draws()
+        self._ahead = None
+        _lib.check(lib.gi_hmcb_stream_begin(self._h, float(self.dt)), "gi_hmcb_stream_begin")
+        self.stream_steps = 0
+        try:
+            while True:
+                for c in range(nc):
+                    while live[c] and inflight[c] < 2 and (max_proposals is None or fed[c] < max_proposals):
+                        L, p0, u = ahead.take(c)
+                        _lib.check(lib.gi_hmcb_stream_feed(self._h, c, L, u, _lib.ptr(p0)),
+                                   "gi_hmcb_stream_feed")
+                        inflight[c] += 1
+                        fed[c] += 1
+                run = C.c_int32()
+                _lib.check(lib.gi_hmcb_stream_runway(self._h, C.byref(run)), "gi_hmcb_stream_runway")
+                if run.value == 0:
+                    break
+                _lib.check(lib.gi_hmcb_stream_advance(self._h, run.value, recs, cap, C.byref(nrec),
+                                                      C.byref(ndone), _lib.ptr(xh)),
+                           "gi_hmcb_stream_advance")
+                self.stream_steps += ndone.value
+                for i in range(nrec.value):
+                    r = recs[i]
+                    c = r.chain
+                    inflight[c] -= 1
+                    if not live[c]:
+                        continue  # a queued proposal that ran after the chain reached its target
+                    acc = bool(r.accept)
+                    self.proposals[c].append((int(r.L), acc))
+                    Udn, Umn = r.U_data / data_size, r.U_model / model_size
+                    Un = Udn + alpha * Umn
+                    if acc:
+                        self.x[c] = xh[i].numpy()
+                        if count[c] >= ndraws and write:
+                            with open(folders[c] + "/misfit.dat", "a") as f:
+                                np.savetxt(f, np.array([[r.U, r.U_data, r.U_model, Un, Udn, Umn, alpha]]),
+                                           fmt="%.8f", delimiter=" ")
+                            x = self.x[c]
+                            if self.constraint == "logarithmic":
+                                mw = (self.low + self.high * np.e ** (self.log_factor * x)) / \
+                                     (1 + np.e ** (self.log_factor * x))
+                            else:
+                                mw = x
+                            with open(folders[c] + "/model.dat", "a") as f:
+                                np.savetxt(f, (self.wminv * mw)[None, :], fmt="%.8f", delimiter=" ")
+                        count[c] += 1
+                        if count[c] >= target:
+                            live[c] = False
+                            ahead.disable(c)
+                    if on_record is not None:
+                        on_record(c, r, acc)
+                    if not self.quiet:
+                        print("chain {}: {:.2%}, misfit(total, data, alpha, model)=({:.7f},{:.7f},{:.2f},"
+                              "{:.7f}) -- accept ratio {:.2%}\n".format(
+                                  c, count[c] / target, Un, Udn, alpha, Umn,
+                                  count[c] / len(self.proposals[c])))
+                        sys.stdout.flush()
+                    if max_proposals is not None and len(self.proposals[c]) >= max_proposals:
+                        live[c] = False
+                        ahead.disable(c)
+        finally:
+            ahead.stop()
+        return self.x
+
     def sample(self, nsamples, ndraws, max_proposals=None):
         """hmc.py:252-343 for every chain of the batch."""
         nc = self.nchains
@@ -322,11 +498,17 @@ class HMCBatch:
 def HMCSampleBatch(model, nchains, nsamples, ndraws, delta, Lrange, initial_model, aprior_model,
                    boundaries, constraint, log_factor, dobs, adaptiveRegul, RegulRate, RegulFactor,
                    regularization, beta, seed, Sigma, nbest=100, save_folder="mychain", rng="numpy",
-                   quiet=False, max_proposals=None):
+                   quiet=False, max_proposals=None, mode="auto"):
     """`hmc.HMCSample` for ranks 0..nchains-1 at once (argument order of hmc.py:358-361, with
     `nchains` inserted after `model` and `myrank` implied by the chain index)."""
     batch = HMCBatch(model, nchains, delta, Lrange, initial_model, aprior_model, boundaries,
                      constraint, log_factor, dobs, RegulFactor, regularization, beta, seed, Sigma,
                      save_folder=save_folder, rng=rng, quiet=quiet)
-    batch.sample(nsamples, ndraws, max_proposals=max_proposals)
+    # "stream": no chain idles (single GPU, host RNG); "lockstep": one proposal per chain per round
+    if mode == "auto":
+        mode = "stream" if (batch._sh is None and rng == "numpy") else "lockstep"
+    if mode == "stream":
+        batch.stream(nsamples, ndraws, max_proposals=max_proposals)
+    else:
+        batch.sample(nsamples, ndraws, max_proposals=max_proposals)
     return batch

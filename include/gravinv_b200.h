@@ -52,6 +52,7 @@ extern "C" {
 #define GI_ERR_CUDA (-2)     /* CUDA runtime error / no device */
 #define GI_ERR_OVERFLOW (-3) /* tesseroid subdivision stack overflow (OverflowError, _tesseroid_numba.py:53-54) */
 #define GI_ERR_NOMEM (-4)
+#define GI_ERR_BUSY (-5)     /* gi_hmcb_stream_feed: the chain already has two proposals queued */
 
 /* regularisers, inversion/potential.py:831-836 */
 #define GI_REG_DAMPING 0
@@ -253,6 +254,30 @@ int gi_hmcb_propose(gi_hmcb *h, const double *p0_host, const int32_t *L_host, do
 /* device draws: chain c uses the Philox key seed + c (like the reference's seed + myrank) */
 int gi_hmcb_propose_philox(gi_hmcb *h, uint64_t seed, uint64_t counter, double sigma,
                            const int32_t *L_host, double dt, gi_hmc_result *results);
+/* Streaming mode: every chain runs its own sequence of proposals back to back.  All chains share
+ * each gradient evaluation (one "batch step"), and a chain that ends a trajectory -- Metropolis test,
+ * commit -- opens its next one inside the same step, so no chain idles while others finish longer
+ * trajectories (hmc.py:295-300 per chain, with each chain's own L sequence).  The host feeds the draws
+ * of up to two proposals per chain ahead of time (L, u = rand(), p0 = randn(M)*Sigma, in the
+ * reference's RNG order) and collects one record per finished proposal.
+ *   begin    -- chains keep their current state (gi_hmcb_set_state); queues are emptied
+ *   feed     -- enqueue one proposal for `chain`; GI_ERR_BUSY if two are already queued
+ *   runway   -- batch steps that can run before some started/fed chain runs out of queued work
+ *   advance  -- run up to nsteps batch steps (fewer if every chain runs dry or the record buffer
+ *               fills); returns the records of the proposals that finished, in completion order;
+ *               x_host (optional, [max_records][M], ideally pinned) receives the chain's current
+ *               position after each finished proposal (the accepted sample when accept == 1). */
+typedef struct {
+    int32_t chain, accept, L, reserved;
+    int64_t seq;                /* index of the proposal within its chain (0, 1, ...) */
+    double U, U_data, U_model;  /* of the state the chain is in AFTER the proposal */
+    double Hcur, Hnew;
+} gi_stream_record;
+int gi_hmcb_stream_begin(gi_hmcb *h, double dt);
+int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u, const double *p0_host);
+int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps);
+int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records, int32_t max_records,
+                           int32_t *nrecords, int32_t *steps_done, double *x_host);
 /* benchmark helper: nsteps leapfrog steps of every chain, no Metropolis; p0_dev is [Cp][ld] or NULL */
 int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t nsteps, double dt);
 int64_t gi_hmcb_launch_count(const gi_hmcb *h);

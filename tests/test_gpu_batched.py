@@ -139,9 +139,11 @@ def test_batched_chains_match_oracle_ranks(golden, name, nchains, tmp_path):
     bt.close()
 
 
-def test_batch_sample_files_match_oracle(golden, tmp_path):
+@pytest.mark.parametrize("mode", ["stream", "lockstep"])
+def test_batch_sample_files_match_oracle(golden, tmp_path, mode):
     """HMCSampleBatch writes, for every chain c, the files the reference process `myrank=c` writes;
-    chains that reach nsamples stop being recorded while the others continue."""
+    chains that reach nsamples stop being recorded while the others continue.  Both schedulers:
+    lockstep rounds and the streaming sampler (chains restart inside the step they finish in)."""
     g = golden["potential_hmc"]
     model, dobs = small_model(g)
     M = model.M
@@ -152,7 +154,7 @@ def test_batch_sample_files_match_oracle(golden, tmp_path):
     bt = batched.HMCSampleBatch(model, nchains, nsamples, 0, args["delta"], args["Lrange"],
                                 np.ones(M) * 0.001, np.ones(M) * 0.001, b, "mandatory", 1000, dobs,
                                 "Fixed", 0.8, args["alpha"], "Damping", args["beta"], args["seed"],
-                                args["Sigma"], save_folder=str(tmp_path / "run"), quiet=True)
+                                args["Sigma"], save_folder=str(tmp_path / "run"), quiet=True, mode=mode)
     om = onp.OracleModel(g["small_Aw"], g["small_wm"], dobs, tuple(g["small_mshape"]))
     lens = set()
     for c in range(nchains):
@@ -167,6 +169,42 @@ def test_batch_sample_files_match_oracle(golden, tmp_path):
         assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
         lens.add(len(ref["log"]))
     assert len(lens) > 1  # the chains needed different numbers of proposals
+    if mode == "stream":
+        # no idling: the batch ran about as many gradient evaluations as the busiest chain needed
+        busiest = max(sum(L for L, _ in bt.proposals[c]) for c in range(nchains))
+        assert busiest <= bt.stream_steps <= busiest + 2 * args["Lrange"][1]
+    bt.close()
+
+
+@pytest.mark.parametrize("name", ["MS", "TV", "fixed", "log"])
+def test_streaming_chains_match_oracle(golden, name, tmp_path):
+    """the streaming scheduler reproduces every chain's proposal log and final state"""
+    g = golden["potential_hmc"]
+    reg, constraint, alpha, beta, delta, Sigma, Lrange, lo, hi, init, fixed = CASES[name]
+    model, dobs = small_model(g, fixed)
+    M = model.M
+    b = np.ones((M, 2))
+    b[:, 0], b[:, 1] = lo, hi
+    nchains, nprops, seed = 7, 5, 11
+    bt = batched.HMCBatch(model, nchains, delta, Lrange, np.ones(M) * init, np.ones(M) * init, b,
+                          constraint, 1000, dobs, alpha, reg, beta, seed, Sigma,
+                          save_folder=str(tmp_path / "st"), quiet=True)
+    recs = []
+    bt.stream(10 ** 6, 0, max_proposals=nprops, write=False,
+              on_record=lambda c, r, acc: recs.append((c, int(r.seq), r.U, r.Hnew)))
+    om = onp.OracleModel(g["small_Aw"], g["small_wm"], dobs, tuple(g["small_mshape"]), fixed=fixed,
+                         grav_fix=g["fixed_gravfix"] if fixed else None)
+    for c in range(nchains):
+        otr = []
+        ref = onp.hmc_sample(om, 10 ** 6, 0, delta, Lrange, np.ones(M) * init, np.ones(M) * init, b,
+                             constraint, 1000, alpha, reg, beta, seed, Sigma, myrank=c,
+                             max_proposals=nprops, trace=otr)
+        assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
+        assert np.max(np.abs(bt.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"]))
+        mine = sorted((seq, Hn) for cc, seq, U, Hn in recs if cc == c)
+        assert [s for s, _ in mine] == list(range(nprops))
+        for (seq, Hn), t in zip(mine, otr):
+            assert abs(Hn - t["Hnew"]) < 1e-9 * abs(t["Hnew"])
     bt.close()
 
 
