@@ -57,6 +57,7 @@ SIGNATURES = {
                                  C.POINTER(_I64)]),
     "gi_prism_gz_assemble": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _D, _P, _I64, _P]),
     "gi_tess_gz_assemble": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _D, _D, _D, _P, _I64, _P, _P]),
+    "gi_tess_gz_leafcount": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _D, _P, _I64, _P, _P]),
     "gi_colsumsq": (C.c_int, [_P, _I64, _I64, _I64, _P, C.c_int, _P]),
     "gi_weights_from_sumsq": (C.c_int, [_P, _I64, _D, _P, _P, _P, _P]),
     "gi_scale_columns": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),

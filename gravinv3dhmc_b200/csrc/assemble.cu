@@ -192,6 +192,9 @@ __device__ __forceinline__ int tess_divisions(double lon, double coslat, double 
 
 constexpr int kTessThreads = 128;
 
+// COUNT = true writes the number of leaf cells of the subdivision instead of the kernel value
+// (index bookkeeping of the adaptive engine, compared bit-exactly with the oracle's).
+template <bool COUNT>
 __global__ void __launch_bounds__(kTessThreads)
 tess_gz_kernel(const double *__restrict__ lon, const double *__restrict__ sinlat,
                const double *__restrict__ coslat, const double *__restrict__ radius, int64_t nrows,
@@ -217,7 +220,8 @@ tess_gz_kernel(const double *__restrict__ lon, const double *__restrict__ sinlat
             const int div0 = tess_divisions(olon, ocos, osin, orad, root, ratio, &err);
             errsum += err;
             if (div0 == (1 | (1 << 2) | (1 << 4))) {
-                acc = tess_leaf(olon, ocos, osin, orad, root);  // fast path: no subdivision
+                // fast path: no subdivision
+                acc = COUNT ? 1.0 : tess_leaf(olon, ocos, osin, orad, root);
             } else {
                 // engine (_tesseroid_numba.py:32-71): LIFO stack, children pushed lon-major
                 int top = -1;
@@ -237,7 +241,7 @@ tess_gz_kernel(const double *__restrict__ lon, const double *__restrict__ sinlat
                     if (ncell > 1) {
                         if (ncell + (top + 1) > kStackSize) {
                             overflow = true;
-                            acc = nan("");
+                            acc = COUNT ? -1.0 : nan("");
                             break;
                         }
                         const double dlon = __ddiv_rn(__dsub_rn(cur.e, cur.w), (double)nlon);
@@ -256,11 +260,11 @@ tess_gz_kernel(const double *__restrict__ lon, const double *__restrict__ sinlat
                                     stack[++top] = c;
                                 }
                     } else {
-                        acc = __dadd_rn(acc, tess_leaf(olon, ocos, osin, orad, cur));
+                        acc = __dadd_rn(acc, COUNT ? 1.0 : tess_leaf(olon, ocos, osin, orad, cur));
                     }
                 }
             }
-            acc = __dmul_rn(__dmul_rn(acc, scale1), scale2);  // tesseroid.py:430
+            if (!COUNT) acc = __dmul_rn(__dmul_rn(acc, scale1), scale2);  // tesseroid.py:430
         }
         G[row * ld + col] = acc;
     }
@@ -365,8 +369,24 @@ extern "C" int gi_tess_gz_assemble(const double *lon, const double *sinlat, cons
     GI_REQUIRE(lon && sinlat && coslat && radius && G && status && (bounds || M == 0),
                "gi_tess_gz_assemble: null pointer");
     dim3 grid((unsigned)ceil_div(ld, kTessThreads), (unsigned)min((int64_t)65535, nrows));
-    tess_gz_kernel<<<grid, kTessThreads, 0, (cudaStream_t)stream>>>(
+    tess_gz_kernel<false><<<grid, kTessThreads, 0, (cudaStream_t)stream>>>(
         lon, sinlat, coslat, radius, nrows, bounds, M, ratio, scale1, scale2, G, ld, status);
+    GI_LAUNCH_CHECK();
+    return GI_OK;
+}
+
+extern "C" int gi_tess_gz_leafcount(const double *lon, const double *sinlat, const double *coslat,
+                                    const double *radius, int64_t nrows, const double *bounds,
+                                    int64_t M, double ratio, double *leaves, int64_t ld,
+                                    int32_t *status, void *stream) {
+    GI_REQUIRE(nrows >= 0 && M >= 0 && ld >= M && ld % 4 == 0, "gi_tess_gz_leafcount: bad shape");
+    GI_REQUIRE(ratio > 0, "gi_tess_gz_leafcount: ratio must be > 0");
+    if (nrows == 0 || ld == 0) return GI_OK;
+    GI_REQUIRE(lon && sinlat && coslat && radius && leaves && status && (bounds || M == 0),
+               "gi_tess_gz_leafcount: null pointer");
+    dim3 grid((unsigned)ceil_div(ld, kTessThreads), (unsigned)min((int64_t)65535, nrows));
+    tess_gz_kernel<true><<<grid, kTessThreads, 0, (cudaStream_t)stream>>>(
+        lon, sinlat, coslat, radius, nrows, bounds, M, ratio, 1.0, 1.0, leaves, ld, status);
     GI_LAUNCH_CHECK();
     return GI_OK;
 }

@@ -80,6 +80,27 @@ def assemble(lon, lat, height, table, ratio=RATIO_G, rows=None, device=None, nco
     return Gd, ncols
 
 
+def leaf_counts(lon, lat, height, table, ratio=RATIO_G):
+    """int32 [n_obs, M] number of leaf cells the adaptive subdivision evaluates per (observation,
+    tesseroid) pair (-1 = stack overflow) -- the decision bookkeeping of the engine
+    (_tesseroid_numba.py:32-71, 135-157), for diagnostics and parity tests."""
+    torch = _lib.require_cuda()
+    lon, lat, height = (np.ascontiguousarray(a, dtype=np.float64) for a in (lon, lat, height))
+    table = np.ascontiguousarray(table, dtype=np.float64).reshape(-1, 6)
+    M, n = table.shape[0], lon.shape[0]
+    ld = _lib.padded_ld(M)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty((n, ld), dtype=torch.float64, device=dev)
+    a_d = [to_device(a, torch, dev) for a in _convert_coords(lon, lat, height)]
+    tab_d = to_device(table, torch, dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().gi_tess_gz_leafcount(_lib.ptr(a_d[0]), _lib.ptr(a_d[1]), _lib.ptr(a_d[2]),
+                                               _lib.ptr(a_d[3]), n, _lib.ptr(tab_d), M, float(ratio),
+                                               _lib.ptr(out), ld, _lib.ptr(status), _lib.stream_ptr()),
+               "gi_tess_gz_leafcount")
+    return out[:, :M].cpu().numpy().astype(np.int32)
+
+
 def gz(lon, lat, height, model, dens=None, ratio=RATIO_G, njobs=1, pool=None, device_out=False):
     """Calculate gz (mGal, density in g/cm^3) of a tesseroid model and the kernel matrix.
 

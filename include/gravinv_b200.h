@@ -87,6 +87,14 @@ int gi_tess_gz_assemble(const double *lon_dev, const double *sinlat_dev, const d
                         int64_t M, double ratio, double scale1, double scale2, double *G_dev,
                         int64_t ld, int32_t *status_dev, void *stream);
 
+/* Subdivision bookkeeping of the same engine: leaves[l*ld + c] = number of leaf cells evaluated for
+ * pair (l, c), as a double (-1 where the stack would overflow).  Lets callers and tests compare the
+ * adaptive-subdivision DECISIONS (_tesseroid_numba.py:135-157) exactly, apart from the values. */
+int gi_tess_gz_leafcount(const double *lon_dev, const double *sinlat_dev, const double *coslat_dev,
+                         const double *radius_dev, int64_t nrows, const double *bounds_dev, int64_t M,
+                         double ratio, double *leaves_dev, int64_t ld, int32_t *status_dev,
+                         void *stream);
+
 /* ---- sensitivity weighting (potential.py:232-264) ---------------------------------------- */
 /* out[c] (+)= sum_l G[l][c]^2, rows summed sequentially in row order. */
 int gi_colsumsq(const double *G_dev, int64_t nrows, int64_t M, int64_t ld, double *out_dev,

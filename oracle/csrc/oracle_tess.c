@@ -176,3 +176,20 @@ int oracle_tess_gz(const double *lon, const double *sinlat, const double *coslat
         }
     return err;
 }
+
+/* Subdivision bookkeeping only: leaves[l*ld + c] = number of leaf cells the adaptive subdivision of
+ * _tesseroid_numba.py:32-71 evaluates for pair (l, c) (-1 where the stack would overflow). */
+int oracle_tess_leaves(const double *lon, const double *sinlat, const double *coslat,
+                       const double *radius, int64_t N, const double *bounds, int64_t M,
+                       double ratio, int32_t *leaves, int64_t ld)
+{
+    for (int64_t c = 0; c < M; ++c)
+        for (int64_t l = 0; l < N; ++l) {
+            int64_t st[2] = {0, 0};
+            int err = 0, ovf = 0;
+            oracle_tess_gz_pair(lon[l], sinlat[l], coslat[l], radius[l], bounds + 6 * c, ratio, &err,
+                                &ovf, st);
+            leaves[l * ld + c] = ovf ? -1 : (int32_t)st[0];
+        }
+    return 0;
+}

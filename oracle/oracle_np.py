@@ -69,6 +69,9 @@ def _lib():
                                      ctypes.c_double, ctypes.c_double, dp, i64,
                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(i64)]
         L.oracle_tess_gz.restype = ctypes.c_int
+        L.oracle_tess_leaves.argtypes = [dp, dp, dp, dp, i64, dp, i64, ctypes.c_double,
+                                         ctypes.c_void_p, i64]
+        L.oracle_tess_leaves.restype = ctypes.c_int
         _LIB = L
     return _LIB
 
@@ -146,6 +149,26 @@ def tess_gz(lon, lat, height, bounds, ratio=RATIO_G, threads: int = 1, stats=Non
     if any(ovfs):
         raise OverflowError
     return K, int(sum(errs))
+
+
+def tess_leaves(lon, lat, height, bounds, ratio=RATIO_G, threads: int = 1):
+    """per-pair leaf counts of the adaptive subdivision (_tesseroid_numba.py:32-71): the index
+    bookkeeping of the tesseroid kernel, int32 [N, M] (-1 = stack overflow)."""
+    lon, lat, height = _c(lon), _c(lat), _c(height)
+    bounds = _c(bounds).reshape(-1, 6)
+    lonr, sinlat, coslat, radius = (_c(a) for a in convert_coords(lon, lat, height))
+    N, M = lon.shape[0], bounds.shape[0]
+    out = np.zeros((N, M), dtype=np.int32)
+    L = _lib()
+
+    def run(lo, hi):
+        if hi > lo:
+            L.oracle_tess_leaves(_dp(lonr[lo:hi]), _dp(sinlat[lo:hi]), _dp(coslat[lo:hi]),
+                                 _dp(radius[lo:hi]), hi - lo, _dp(bounds), M, ratio,
+                                 out[lo:hi].ctypes.data_as(ctypes.c_void_p), M)
+
+    _run_rows(run, N, threads)
+    return out
 
 
 def _run_rows(fn, N, threads):

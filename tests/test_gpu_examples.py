@@ -22,7 +22,8 @@ def normwise(a, b):
     return np.max(np.abs(a - b)) / np.max(np.abs(b))
 
 
-def check_chains(g, key, model, dobs, nsamples, delta, init, apr, bounds, alpha, reg, beta, Sigma, tmp_path):
+def check_chains(g, key, model, dobs, nsamples, delta, init, apr, bounds, alpha, reg, beta, Sigma, tmp_path,
+                 rtol=1e-8):
     """both ranks at once through the batched sampler, rank 0 also through the single-chain path"""
     M = model.M
     b = np.ones((M, 2))
@@ -37,14 +38,14 @@ def check_chains(g, key, model, dobs, nsamples, delta, init, apr, bounds, alpha,
         assert [(L, int(a)) for L, a in bt.proposals[rank]] == [(int(L), int(a)) for L, a in log]
         mis = np.loadtxt(tmp_path / f"{key}_{reg}_b{rank}" / "misfit.dat", ndmin=2)
         mod = np.loadtxt(tmp_path / f"{key}_{reg}_b{rank}" / "model.dat", ndmin=2)
-        assert np.allclose(mis, g[f"{key}_{reg}_r{rank}_misfit"], rtol=1e-8, atol=2e-8)
-        assert np.allclose(mod[-1], g[f"{key}_{reg}_r{rank}_last_model"], rtol=0, atol=2e-8)
+        assert np.allclose(mis, g[f"{key}_{reg}_r{rank}_misfit"], rtol=rtol, atol=2e-8)
+        assert np.allclose(mod[-1], g[f"{key}_{reg}_r{rank}_last_model"], rtol=0, atol=max(2e-8, rtol))
     bt.close()
     ch = hmc.HMCSample(model, nsamples, 0, delta, [5, 20], init, apr, b, "mandatory", 1000, dobs,
                        "Fixed", 0.8, alpha, reg, beta, 100, Sigma, myrank=1,
                        save_folder=str(tmp_path / f"{key}_{reg}_s"), quiet=True)
     mis = np.loadtxt(tmp_path / f"{key}_{reg}_s1" / "misfit.dat", ndmin=2)
-    assert np.allclose(mis, g[f"{key}_{reg}_r1_misfit"], rtol=1e-8, atol=2e-8)
+    assert np.allclose(mis, g[f"{key}_{reg}_r1_misfit"], rtol=rtol, atol=2e-8)
     ch.close()
 
 
@@ -90,18 +91,34 @@ def test_c3_realdata(golden, tmp_path, monkeypatch):
                                     mtopo=(t[:, 0], t[:, 1], t[:, 2]), verbose=False)
     assert model.mshape == tuple(g["c3_mshape"])
     assert np.array_equal(np.array(model.mask), g["c3_mask"])  # bit-exact bookkeeping
-    assert np.allclose(model.Wm.diagonal(), g["c3_wm"], rtol=1e-11)
-    assert normwise(model.Aw.cpu().numpy()[g["c3_rows"]], g["c3_Aw_rows"]) < 1e-10
+    # The observations of this data set sit ON the 0.5-degree cell corners and inside the top layer,
+    # so ~1.4 % of the pairs subdivide and some reach 100+ leaves a few hundred metres from the
+    # observation.  There l^2 = r^2 + rc^2 - 2 r rc cos(psi) cancels ~(r/l)^2 ~ 1e9-fold: a 1-ulp
+    # difference between CUDA's and glibc's cos() moves those leaf values by up to ~1e-6 relative --
+    # in the reference itself as much as here.  Parity is therefore stated as: subdivision DECISIONS
+    # bit-exact for every pair, values 1e-10 wherever the pair has < 9 leaves (98.6 % of the entries
+    # that subdivide at all), and <= 1e-5 relative on the deeply subdivided near-field pairs.
+    tab = model.mesh.bounds_table()
+    Kraw, _ = tesseroid.assemble(o[:, 0], o[:, 1], o[:, 2], tab)
+    K = Kraw[:, : model.M].cpu().numpy()
+    Ko, _ = onp.tess_gz(o[:, 0], o[:, 1], o[:, 2], tab, threads=8)
+    leaves = tesseroid.leaf_counts(o[:, 0], o[:, 1], o[:, 2], tab)
+    assert np.array_equal(leaves, onp.tess_leaves(o[:, 0], o[:, 1], o[:, 2], tab, threads=8))
+    rel = np.abs(K - Ko) / np.abs(Ko)
+    assert rel[leaves < 9].max() < 1e-10
+    assert rel.max() < 1e-5 and (rel > 1e-10).sum() < 2e-4 * rel.size
+    assert np.allclose(model.Wm.diagonal(), g["c3_wm"], rtol=1e-6)
+    assert normwise(model.Aw.cpu().numpy()[g["c3_rows"]], g["c3_Aw_rows"]) < 1e-6
     M = model.M
     init = utils.rho2carve(np.ones(int(np.prod(model.mshape))) * 0.01, model.mask)
     apr = utils.rho2carve(g["c3_apr_mesh"], model.mask)
     U, gr, dpre, Ud, Um = model.misfit_and_grad(model.Wm @ init, model.Wm @ apr, None, None, "mandatory",
                                                 1000, 1, regulization="MS", beta=0.01)
-    assert np.allclose([U, Ud, Um, gr[0], gr[M // 2], np.linalg.norm(gr)], g["c3_mg_MS"], rtol=1e-9)
-    assert normwise(dpre, g["c3_mg_dpre"]) < 1e-10
+    assert np.allclose([U, Ud, Um, gr[0], gr[M // 2], np.linalg.norm(gr)], g["c3_mg_MS"], rtol=1e-6)
+    assert normwise(dpre, g["c3_mg_dpre"]) < 1e-6
     for reg in ("Damping", "MS"):
         check_chains(g, "c3", model, dobs, 3, float(g[f"c3_{reg}_delta"]), init, apr, (-0.5, 0.5), 1,
-                     reg, 0.01, 0.01, tmp_path)
+                     reg, 0.01, 0.01, tmp_path, rtol=1e-6)
     with pytest.raises(ValueError, match="Smoothness/TV"):  # carved model: no full grid
         b = np.ones((M, 2))
         hmc.HMCSample(model, 1, 0, 0.01, [5, 20], init, apr, b, "mandatory", 1000, dobs, "Fixed", 0.8,
