@@ -88,8 +88,10 @@ class GravMagModule:
             Apad, M = tesseroid.assemble(self.lonobs, self.latobs, self.heightobs, table,
                                          rows=self.rows, ncols=ncols)
         else:
-            Apad, M = prism.assemble(self.lonobs, self.latobs, self.heightobs, table,
-                                     rows=self.rows)
+            # structured meshes share their corners: one evaluation per mesh node (bit-identical)
+            out = prism.assemble_grid(self.lonobs, self.latobs, self.heightobs, mesh, rows=self.rows)
+            Apad, M = out if out is not None else prism.assemble(
+                self.lonobs, self.latobs, self.heightobs, table, rows=self.rows)
         self._lap(ev, "assemble_ms")
         self._say("kernel.shape ({}, {})".format(n_total, M))
         self._say("End of calculate kernel:%.6f s" % (time.time() - start))

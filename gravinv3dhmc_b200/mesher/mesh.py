@@ -47,6 +47,26 @@ class _MeshBase:
             z1[k], z2[k] = self._layer(k)
         return x1, x2, y1, y2, z1, z2
 
+    def node_axes(self):
+        """(xn, yn, zn) node coordinates per axis when neighbouring cells share their edges bit for
+        bit (upper edge of cell i == lower edge of cell i+1 as doubles on every axis), else None.
+        When they do, a corner of the mesh is one point for all the cells around it and the
+        assembly kernel may evaluate it once (gi_prism_gz_assemble_grid)."""
+        x1, x2, y1, y2, z1, z2 = self._axis_edges()
+        for lo, hi in ((x1, x2), (y1, y2), (z1, z2)):
+            if not np.array_equal(hi[:-1], lo[1:]):
+                return None
+        return (np.append(x1, x2[-1]), np.append(y1, y2[-1]), np.append(z1, z2[-1]))
+
+    def column_map(self):
+        """int32 [size]: column of G for every cell (-1 = masked), or None when nothing is masked"""
+        if not len(self.mask):
+            return None
+        m = self._mask_array()
+        cm = np.full(self.size, -1, dtype=np.int32)
+        cm[~m] = np.arange(int((~m).sum()), dtype=np.int32)
+        return cm
+
     def _mask_array(self):
         """boolean [size] array of masked cells (cached against the mask list's length)"""
         key = len(self.mask)

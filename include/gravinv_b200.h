@@ -77,6 +77,19 @@ int gi_prism_gz_assemble(const double *xp_dev, const double *yp_dev, const doubl
                          int64_t nrows, const double *bounds_dev, int64_t M, double scale,
                          double *G_dev, int64_t ld, void *stream);
 
+/* Same result for a STRUCTURED prism mesh (mesher/mesh.py PrismMesh / PrismMeshSegment) whose cells
+ * share their edges bit for bit: xn[nx+1], yn[ny+1], zn[nz+1] are the node coordinates per axis
+ * (cell (k,j,i) spans xn[i]..xn[i+1] etc.; flat cell index (k*ny + j)*nx + i as in mesh.py:229-236).
+ * The corner term is evaluated once per node and shared by the up to 8 cells around it, in the
+ * reference's summation order -> bit-identical to gi_prism_gz_assemble, ~5x fewer evaluations.
+ * colmap_dev (optional, int32 [nx*ny*nz]) maps a cell to its column (-1 = carved out); without it
+ * M must equal nx*ny*nz.  Columns [M, ld) are zeroed. */
+int gi_prism_gz_assemble_grid(const double *xp_dev, const double *yp_dev, const double *zp_dev,
+                              int64_t nrows, const double *xn_dev, const double *yn_dev,
+                              const double *zn_dev, int32_t nx, int32_t ny, int32_t nz,
+                              const int32_t *colmap_dev, int64_t M, double scale, double *G_dev,
+                              int64_t ld, void *stream);
+
 /* Tesseroid gz, 2x2x2 Gauss-Legendre with the reference's LIFO adaptive subdivision.
  * Inputs are the converted coordinates of gravmag/tesseroid.py:109-123.
  * status_dev is int32[2]: [0] accumulates the reference's error_code (-1 per refused split),

@@ -237,3 +237,44 @@ def test_config1_weights(golden):
                                     (o[:, 0], o[:, 1], o[:, 2]), verbose=False)
     assert np.allclose(model.Wm.diagonal(), c["c1_wm"], rtol=1e-12)
     assert normwise(model.Aw.cpu().numpy()[p["c1_rows"]], c["c1_Aw_rows"]) < TOL
+
+
+@pytest.mark.parametrize("case", ["uniform", "uniform_ragged", "segment", "carved", "config1"])
+def test_structured_grid_assembly_is_bit_identical(case, golden, tmp_path, monkeypatch):
+    """gi_prism_gz_assemble_grid (one corner evaluation per mesh node, shared by the cells around it)
+    returns exactly the bits of the per-cell kernel; meshes whose cells do not share their edges bit
+    for bit fall back to the per-cell kernel."""
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(3)
+    if case == "uniform":
+        mesh = mesher.PrismMesh((0, 6400, 0, 800, 0, 800), (100, 100, 100))      # 8 x 8 x 64
+    elif case == "uniform_ragged":
+        mesh = mesher.PrismMesh((0, 3700, 0, 900, 0, 500), (100, 100, 100))      # 5 x 9 x 37: edge tiles
+    elif case == "segment":
+        mesh = mesher.PrismMeshSegment((0, 2000, 0, 3000, 0, 2100), ([100, 200, 300], 100, 100),
+                                       [0, 300, 900, 2100])
+    elif case == "carved":
+        mesh = mesher.PrismMesh((0, 400, 0, 600, 0, 500), (100, 100, 100))
+        t = golden["prism"]["carved_topo"]
+        mesh.carvetopo(t[:, 0], t[:, 1], t[:, 2])
+        assert len(mesh.mask) > 0
+    else:
+        mesh = mesher.PrismMesh((0, 2000, 0, 3000, 0, 1000), (100, 100, 100))
+    b = mesh.bounds
+    n = 37
+    xp, yp = rng.uniform(b[0] - 200, b[1] + 200, n), rng.uniform(b[2] - 200, b[3] + 200, n)
+    zp = rng.uniform(-300, -0.5, n)
+    if case == "config1":  # the example's observations lie ON the mesh top and on cell edges
+        o = golden["prism"]["c1_obs"]
+        xp, yp, zp = o[::17, 0], o[::17, 1], o[::17, 2]
+    out = prism.assemble_grid(xp, yp, zp, mesh)
+    assert out is not None
+    Gg, Mg = out
+    Gc, Mc = prism.assemble(xp, yp, zp, mesh.bounds_table())
+    assert Mg == Mc == mesh.size - len(mesh.mask)
+    assert torch.equal(Gg, Gc)
+    Gs, _ = prism.assemble_grid(xp, yp, zp, mesh, rows=(5, 30))
+    assert torch.equal(Gs, Gc[5:30])
+    # meshes without bit-identical shared edges do not qualify
+    assert prism.assemble_grid(xp, yp, zp, mesher.PrismMesh((0, 400, 0, 600, 0, 500), (37.3, 41.7, 33.1))) is None
+    assert prism.assemble_grid(xp, yp, zp, mesher.PrismMesh((0, 1000, 0, 1000, 0, 3000), (100, 100, 100), ratio=1.3)) is None

@@ -41,7 +41,10 @@ if a.kind == "prism":
     X, Y = np.meshgrid(xs, np.linspace(50, ny * 100 - 50, side))
     tab = mesh.bounds_table()
     t, (G, M) = timeit(lambda: prism.assemble(X.ravel(), Y.ravel(), np.full(X.size, -1.0), tab))
-    print("prism  %d obs x %d cells: %.3f s  %.1f Mpairs/s" % (X.size, M, t, X.size * M / t / 1e6))
+    print("prism per-cell kernel   %d obs x %d cells: %.3f s  %.1f Mpairs/s" % (X.size, M, t, X.size * M / t / 1e6))
+    t, (G2, M) = timeit(lambda: prism.assemble_grid(X.ravel(), Y.ravel(), np.full(X.size, -1.0), mesh))
+    print("prism shared-node kernel %d obs x %d cells: %.3f s  %.1f Mpairs/s  bit-identical: %s"
+          % (X.size, M, t, X.size * M / t / 1e6, torch.equal(G, G2)))
 else:
     if (a.scale or "c4") == "c4":
         mesh = mesher.TesseroidMesh((-180, 180, -90, 90, 0, -3000000), (-300000, 3, 3))
