@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -276,21 +276,18 @@ def gpu_arm(args):
                               HMC["regularization"], HMC["beta"], HMC["seed"], HMC["Sigma"],
                               save_folder=os.path.join(tempfile.gettempdir(), "gi_bench_chain"),
                               quiet=True)
-        cp = int(lib.gi_hmcb_padded_chains(bt._h)) if world == 1 else bt._sh.eng.Cp
+        cp = int(lib.gi_hmcb_padded_chains(bt._h))
         gen = torch.Generator(device=dev)
         gen.manual_seed(HMC["seed"])
         p0b = torch.zeros((cp, model.ld), dtype=torch.float64, device=dev)
         p0b[:nch, :M] = torch.randn((nch, M), dtype=torch.float64, device=dev, generator=gen) * HMC["Sigma"]
 
         def run_steps(k):
-            if world == 1:
-                _lib.check(lib.gi_hmcb_leapfrog_steps(bt._h, _lib.ptr(p0b), int(k), float(dt)),
-                           "gi_hmcb_leapfrog_steps")
-            else:
-                bt._sh.leapfrog_steps(p0b, k)
+            _lib.check(lib.gi_hmcb_leapfrog_steps(bt._h, _lib.ptr(p0b), int(k), float(dt)),
+                       "gi_hmcb_leapfrog_steps")
 
         def launch_count():
-            return int(lib.gi_hmcb_launch_count(bt._h)) if world == 1 else int(bt._sh.eng.launches)
+            return int(lib.gi_hmcb_launch_count(bt._h))
     elif world == 1:
         chain._ensure_handle(alpha)
         chain._sync_state(x0)
@@ -408,48 +405,37 @@ def gpu_arm(args):
     if nch > 1:
         # public batched call: per proposal the host draws L, p0 (randn) and u for every chain in the
         # reference's RNG order, p0 goes host->device, accepted states come back device->host
-        if world == 1:
-            bt.start_draws(wait=True)  # the first two proposals' random numbers are ready up front
+        bt.start_draws(wait=True)  # the first two proposals' random numbers are ready up front
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=group)
         t0 = time.perf_counter()
-        if world == 1:
-            # streaming sampler: chains restart inside the step they finish in (no idling); the
-            # draws are prepared on a host thread while the GPU runs
-            # measured over the steady-state window that ends when the first chain has completed its
-            # quota of proposals (after that the batch drains and chains run dry one by one)
-            nprop = max(2, int(round(args.steps / 12.5)) + 1)
-            bt.proposals = [[] for _ in range(nch)]
-            window = {}
+        # streaming sampler: chains restart inside the step they finish in (no idling); the draws are
+        # prepared on host threads while the GPU runs.  Measured over the steady-state window that
+        # ends when the first chain has completed its quota of proposals (after that the batch
+        # drains and chains run dry one by one).
+        nprop = max(2, int(round(args.steps / 12.5)) + 1)
+        bt.proposals = [[] for _ in range(nch)]
+        window = {}
 
-            def on_record(c, r, acc):
-                if not window and len(bt.proposals[c]) >= nprop:
-                    torch.cuda.synchronize()
-                    window.update(t=time.perf_counter() - t0, steps=bt.stream_steps,
-                                  props=sum(len(q) for q in bt.proposals))
+        def on_record(c, r, acc):
+            if not window and len(bt.proposals[c]) >= nprop:
+                torch.cuda.synchronize()
+                window.update(t=time.perf_counter() - t0, steps=bt.stream_steps,
+                              props=sum(len(q) for q in bt.proposals))
 
-            bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
-            api = ("HMCBatch.stream -> gi_hmcb_stream_feed/advance (host RNG in the reference's order, "
-                   "per-chain L in [5,20], chains restart inside the step they finish in; steady-state "
-                   "window of %d batch steps)" % window["steps"])
-        else:
-            done, nprop = 0, 0
-            while done < args.steps:
-                out = bt.propose()
-                done += int(np.mean([o[1] for o in out]))
-                nprop += 1
-            api = ("HMCBatch.propose (row-sharded lockstep rounds, host RNG; chains with short "
-                   "trajectories idle until the longest ends)")
+        bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
+        api = ("HMCBatch.stream -> gi_hmcb_stream_feed/advance (host RNG in the reference's order, "
+               "per-chain L in [5,20], chains restart inside the step they finish in; steady-state "
+               "window of %d batch steps%s)" % (window["steps"], "; row-sharded, NCCL all-reduce hooks"
+                                               if world > 1 else ""))
         torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
+        # every chain takes one leapfrog step per batch step inside the window
+        steps_done, t_e2e, nprops_done = nch * window["steps"], window["t"], window["props"]
         if world > 1:
             t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
             t_e2e = float(t[0])
-        steps_done = sum(L for c in range(nch) for (L, _) in bt.proposals[c])
-        nprops_done = sum(len(bt.proposals[c]) for c in range(nch))
-        if world == 1:
-            # every chain takes one leapfrog step per batch step inside the window
-            steps_done, t_e2e, nprops_done = nch * window["steps"], window["t"], window["props"]
         e2e = {"value": steps_done / t_e2e, "unit": "leapfrog steps/s",
                "h2d_bytes_per_step": int(nprops_done * (8 * M + 12) / steps_done),
                "d2h_bytes_per_step": int(nprops_done * (8 * M + 80) / steps_done),

@@ -101,6 +101,7 @@ SIGNATURES = {
     "gi_hmcb_get_misfit": (C.c_int, [_P, _P, _P, _P, _P]),
     "gi_hmcb_propose": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P]),
     "gi_hmcb_propose_philox": (C.c_int, [_P, C.c_uint64, C.c_uint64, _D, _P, _D, _P]),
+    "gi_hmcb_set_shard": (C.c_int, [_P, _I64, _P, _P, C.c_int32, _P, _P, _P]),
     "gi_hmcb_stream_begin": (C.c_int, [_P, _D]),
     "gi_hmcb_stream_feed": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _P]),
     "gi_hmcb_stream_runway": (C.c_int, [_P, C.POINTER(C.c_int32)]),
@@ -120,6 +121,8 @@ SIGNATURES = {
     "gi_hmc_set_wavelet": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _I64]),
     "gi_csr_spmv": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
 }
+
+SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
 
 _LIB = None
 

@@ -200,7 +200,8 @@ gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
 template <int NT, int WC>
 __global__ void __launch_bounds__(kGemmThreads * WC, 1)
 gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ R, int64_t npad,
-                int64_t nrows, double *__restrict__ out) {
+                int64_t nrows, double *__restrict__ out, int64_t strip0, int64_t out_ld,
+                int64_t out_col0) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = kGemmThreads * WC;
     constexpr int C = 8 * NT;
@@ -210,7 +211,9 @@ gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
     constexpr int GU = kAdjK * 128 / T;  // Aw chunks per thread per stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int wv = warp & 7, wc = warp >> 3;  // voxel group, chain half
-    const int64_t v0 = (int64_t)blockIdx.x * kAdjCols;
+    // strips [strip0, strip0 + gridDim.x) of the matrix; the output of this launch is a [C][out_ld]
+    // block whose column 0 is matrix column out_col0 (one "piece" of the piece-major layout)
+    const int64_t v0 = (strip0 + blockIdx.x) * kAdjCols;
     const int ntiles = (int)(npad / kAdjK);
 
     // copy slots: Aw rows (tid>>7) + (T/128)u of the stage, 16-B chunk tid&127 of the 256-voxel strip.
@@ -304,7 +307,7 @@ gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
             for (int j = 0; j < NTW; ++j)
 #pragma unroll
                 for (int e2 = 0; e2 < 2; ++e2) {
-                    double *dst = out + (int64_t)(8 * (wc * NTW + j) + 2 * t + e2) * ld + v;
+                    double *dst = out + (int64_t)(8 * (wc * NTW + j) + 2 * t + e2) * out_ld + (v - out_col0);
                     asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(dst), "d"(acc[2 * h][j][e2]),
                                  "d"(acc[2 * h + 1][j][e2])
                                  : "memory");
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(kUpdThreads) update_batched_kernel(UpdateArgs 
     }
     const int64_t off = c * ctl.vec_stride;
     if (a.grad_in) a.grad_in += off;
-    if (a.gpart) a.gpart += off;
+    if (a.gpart) a.gpart += a.gp_ldk ? c * a.gp_ldk : off;
     a.x_in += off;
     a.mw_in += off;
     a.p += off;
@@ -536,6 +539,15 @@ __global__ void commit_stream_kernel(const DevState *__restrict__ st, StreamCtl 
     if (j < N) d_cur[c * N + j] = d[c * N + j];
 }
 
+// sums[c][col] <-> red[off + c] (contiguous buffers for the scalar all-reduces of the sharded mode)
+__global__ void pack_sums_kernel(const double *__restrict__ sums, double *__restrict__ red, int C,
+                                 int col, int off, int unpack) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (unpack) const_cast<double *>(sums)[8 * c + col] = red[off + c];
+    else red[off + c] = sums[8 * c + col];
+}
+
 __global__ void set_u_kernel(DevState *st, const double *__restrict__ u, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) st[c].u = u[c];
@@ -620,12 +632,19 @@ int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream
     return GI_OK;
 }
 
-int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s) {
-    const unsigned grid = (unsigned)p->b_strips;
+// npieces > 1: `out` is piece-major [npieces][C][ld / npieces]; this launch fills piece `piece`
+int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s,
+                        int piece, int npieces) {
+    const int64_t ldk = p->ld / npieces;
+    const int64_t strips = npieces == 1 ? p->b_strips : ldk / kAdjCols;
+    const int64_t strip0 = piece * strips;
+    const unsigned grid = (unsigned)strips;
+    double *outp = out + (int64_t)piece * p->b_C * ldk;
+    const int64_t col0 = piece * ldk;
 #define GI_ADJ(NT)                                                                             \
     gemm_adj_kernel<NT, WarpSplit<NT>::adj>                                                    \
         <<<grid, kGemmThreads * WarpSplit<NT>::adj, kStages * adj_stage_bytes<NT>(), s>>>(     \
-        G, p->ld, R, p->b_npad, p->nrows, out)
+        G, p->ld, R, p->b_npad, p->nrows, outp, strip0, ldk, col0)
     switch (p->b_nt) {
         case 1: GI_ADJ(1); break;
         case 2: GI_ADJ(2); break;
@@ -658,6 +677,7 @@ int gi::launch_update_batched(gi_plan *p, const gi_reg_params *reg, const double
     a.p = pm; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;
     a.dt = dt; a.M = p->M; a.ld = p->ld; a.reg = *reg;
     a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = sums;
+    if (gdata) { a.gp_ldk = p->b_gp_ldk; a.gp_piece_stride = p->b_gp_piece_stride; }
     BatchCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
     ctl.L = L_dev; ctl.step = step; ctl.uniform_mode = uniform_mode; ctl.vec_stride = p->ld;
@@ -762,6 +782,12 @@ struct gi_hmcb {
     gi_stream_record *rec_dev, *rec_host;
     int64_t rec_cap;
     double *s_xin, *s_xout, *s_mwin, *s_mwout;
+    // row-sharded mode (gi_hmcb_set_shard)
+    int64_t n_total;
+    gi_shard_hook hook;
+    void *hook_user;
+    double *g_ext, *red;  // caller-owned piece-major gradient buffer and [2*C] scalar buffer
+    int npieces;
 };
 
 static void hmcb_free(gi_hmcb *h) {
@@ -808,6 +834,8 @@ extern "C" int gi_hmcb_create(const gi_hmc_config *cfg, int32_t nchains, const d
     h->cfg = *cfg;
     h->G = G;
     h->nchains = nchains;
+    h->n_total = cfg->N;
+    h->npieces = 1;
     h->stream = (cudaStream_t)stream;
     rc = gi_plan_create(cfg->N, cfg->M, cfg->ld, nchains, &h->plan);
     if (rc) { delete h; return rc; }
@@ -891,23 +919,80 @@ extern "C" int gi_hmcb_set_reg(gi_hmcb *h, const gi_reg_params *reg) {
     return GI_OK;
 }
 
+// d, r, sums[.][0..1] and the gradient partials for the positions mw_in; in row-sharded mode the two
+// exchange steps go through the caller's hook and the adjoint output is reduced piece by piece
+// while the next piece is being computed
+static int hb_data_pass(gi_hmcb *h, const double *mw_in) {
+    gi_plan *p = h->plan;
+    cudaStream_t s = h->stream;
+    const double *fix = h->cfg.fixed ? h->fix : nullptr;
+    int rc = launch_gemm_fwd(p, h->G, mw_in, s);
+    if (rc) return rc;
+    if (!h->hook) {
+        rc = launch_misfit_batched(p, 0, p->nrows, h->d, fix, h->dobs_c, h->r, h->sums, s);
+        if (!rc) rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
+        h->launches += 3;
+        return rc;
+    }
+    const int C = (int)h->C;
+    rc = launch_misfit_batched(p, 1, h->n_total, h->d, fix, h->dobs_c, h->r, h->sums, s);
+    if (rc) return rc;
+    pack_sums_kernel<<<1, 64, 0, s>>>(h->sums, h->red, C, 0, 0, 0);
+    GI_LAUNCH_CHECK();
+    GI_REQUIRE(h->hook(h->hook_user, 0, 0, 0) == 0, "shard hook failed (data sums)");
+    pack_sums_kernel<<<1, 64, 0, s>>>(h->sums, h->red, C, 0, 0, 1);
+    GI_LAUNCH_CHECK();
+    rc = launch_misfit_batched(p, 2, h->n_total, h->d, fix, h->dobs_c, h->r, h->sums, s);
+    if (rc) return rc;
+    pack_sums_kernel<<<1, 64, 0, s>>>(h->sums, h->red, C, 1, C, 0);
+    GI_LAUNCH_CHECK();
+    GI_REQUIRE(h->hook(h->hook_user, 2, 0, 1) == 0, "shard hook failed (residual norms)");
+    for (int pc = 0; pc < h->npieces; ++pc) {
+        rc = launch_gemm_adj(p, h->G, h->r, h->g_ext, s, pc, h->npieces);
+        if (rc) return rc;
+        GI_REQUIRE(h->hook(h->hook_user, 1, pc, 1) == 0, "shard hook failed (gradient piece)");
+    }
+    GI_REQUIRE(h->hook(h->hook_user, 3, 0, 0) == 0, "shard hook failed (wait)");
+    pack_sums_kernel<<<1, 64, 0, s>>>(h->sums, h->red, C, 1, C, 1);
+    GI_LAUNCH_CHECK();
+    h->launches += 7 + h->npieces;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_set_shard(gi_hmcb *h, int64_t n_total, const double *dobs_c_host,
+                                 double *gdata_dev, int32_t npieces, double *red_dev,
+                                 gi_shard_hook hook, void *user) {
+    GI_REQUIRE(h && hook && gdata_dev && red_dev && dobs_c_host, "gi_hmcb_set_shard: null pointer");
+    GI_REQUIRE(n_total >= h->cfg.N, "gi_hmcb_set_shard: n_total is the GLOBAL observation count");
+    GI_REQUIRE(npieces >= 1 && h->cfg.ld % npieces == 0 && (npieces == 1 || (h->cfg.ld / npieces) % kAdjCols == 0),
+               "gi_hmcb_set_shard: ld / npieces must be a multiple of 256");
+    GI_CUDA(cudaMemcpyAsync(h->dobs_c, dobs_c_host, sizeof(double) * h->cfg.N, cudaMemcpyHostToDevice,
+                            h->stream));
+    GI_CUDA(cudaStreamSynchronize(h->stream));
+    h->n_total = n_total;
+    h->hook = hook;
+    h->hook_user = user;
+    h->g_ext = gdata_dev;
+    h->red = red_dev;
+    h->npieces = npieces;
+    h->plan->b_gp_ldk = h->cfg.ld / npieces;
+    h->plan->b_gp_piece_stride = h->C * (h->cfg.ld / npieces);
+    h->has_state = false;
+    return GI_OK;
+}
+
 // one batched misfit_and_grad at (x_in, mw_in) + the fused update
 static int hb_grad_eval_and_update(gi_hmcb *h, const double *x_in, const double *mw_in, double *x_out,
                                    double *mw_out, double *grad_out, double dt, const int32_t *L_dev,
                                    int step, int uniform_mode) {
     gi_plan *p = h->plan;
     cudaStream_t s = h->stream;
-    int rc = launch_gemm_fwd(p, h->G, mw_in, s);
+    int rc = hb_data_pass(h, mw_in);
     if (rc) return rc;
-    rc = launch_misfit_batched(p, 0, p->nrows, h->d, h->cfg.fixed ? h->fix : nullptr, h->dobs_c, h->r,
-                               h->sums, s);
-    if (rc) return rc;
-    rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
-    if (rc) return rc;
-    rc = launch_update_batched(p, &h->cfg.reg, nullptr, h->gdata, x_in, mw_in, h->mwapr, h->wmsq,
-                               h->low, h->high, h->p, x_out, mw_out, grad_out, dt, L_dev, step,
-                               uniform_mode, h->sums, s);
-    h->launches += 4;
+    rc = launch_update_batched(p, &h->cfg.reg, nullptr, h->hook ? h->g_ext : h->gdata, x_in, mw_in,
+                               h->mwapr, h->wmsq, h->low, h->high, h->p, x_out, mw_out, grad_out, dt,
+                               L_dev, step, uniform_mode, h->sums, s);
+    h->launches += 1;
     return rc;
 }
 
@@ -1170,6 +1255,7 @@ static int launch_update_modes(gi_hmcb *h, const double *grad_in, const double *
     a.high = h->high; a.p = h->p; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;
     a.dt = h->stream_dt; a.M = p->M; a.ld = p->ld; a.reg = h->cfg.reg;
     a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = h->sums;
+    if (gdata) { a.gp_ldk = p->b_gp_ldk; a.gp_piece_stride = p->b_gp_piece_stride; }
     BatchCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
     ctl.vec_stride = p->ld; ctl.nblocks = p->upd_blocks; ctl.use_modes = 1;
@@ -1191,7 +1277,6 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
     GI_REQUIRE(h && h->streaming && nrecords, "gi_hmcb_stream_advance: not streaming");
     GI_REQUIRE(nsteps >= 0 && max_records >= 0 && (records || max_records == 0),
                "gi_hmcb_stream_advance: bad argument");
-    gi_plan *p = h->plan;
     cudaStream_t s = h->stream;
     const int64_t M = h->cfg.M, ld = h->cfg.ld, N = h->cfg.N;
     const int C = (int)h->C;
@@ -1240,15 +1325,11 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         if (!any_active && !any_start) break;  // every chain ran dry
         int rc = GI_OK;
         if (any_active) {
-            rc = launch_gemm_fwd(p, h->G, h->s_mwin, s);
+            rc = hb_data_pass(h, h->s_mwin);
             if (!rc)
-                rc = launch_misfit_batched(p, 0, p->nrows, h->d, h->cfg.fixed ? h->fix : nullptr,
-                                           h->dobs_c, h->r, h->sums, s);
-            if (!rc) rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
-            if (!rc)
-                rc = launch_update_modes(h, nullptr, h->gdata, h->s_xin, h->s_mwin, h->s_xout,
-                                         h->s_mwout, h->gnew, modeA, nullptr);
-            h->launches += 4;
+                rc = launch_update_modes(h, nullptr, h->hook ? h->g_ext : h->gdata, h->s_xin,
+                                         h->s_mwin, h->s_xout, h->s_mwout, h->gnew, modeA, nullptr);
+            h->launches += 1;
             if (rc) return rc;
         }
         if (any_fin || any_start) {

@@ -23,6 +23,7 @@ struct gi_plan {
     double *b_blockpart;      // [b_C][upd_blocks][3]
     double *b_scratch_sums;   // [b_C][8]
     unsigned int *b_counter;  // [b_C]
+    int64_t b_gp_ldk, b_gp_piece_stride;  // piece-major adjoint output (0 = plain [b_C][ld])
 };
 
 
@@ -50,6 +51,10 @@ struct UpdateArgs {
     double *sums;           // [2] = Um, [3] = K after update, [4] = K before update
     int save_k0;            // also park K before the update in sums[5] (opening half step)
     const double *p_in;     // momentum is read from here (written to p) when non-null
+    // piece-major gradient partials (row-sharded batches all-reduce the adjoint output piece by
+    // piece): element j of a chain lives at gpart[(j / gp_ldk) * gp_piece_stride + j % gp_ldk];
+    // gp_ldk == 0 means the plain [ld] layout
+    int64_t gp_ldk, gp_piece_stride;
 };
 
 int check_reg(const gi_reg_params *reg, int64_t M);
@@ -57,7 +62,8 @@ int check_reg(const gi_reg_params *reg, int64_t M);
 int batched_plan_init(gi_plan *p);
 void batched_plan_free(gi_plan *p);
 int launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s);
-int launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s);
+int launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s,
+                    int piece = 0, int npieces = 1);
 int launch_misfit_batched(gi_plan *p, int mode, int64_t n_total, double *d, const double *fix,
                           const double *dobs_c, double *r, double *sums, cudaStream_t s);
 int launch_update_batched(gi_plan *p, const gi_reg_params *reg, const double *grad_in,
@@ -84,7 +90,12 @@ __device__ __forceinline__ void update_body(const UpdateArgs &a, bool copy_x) {
             grad = a.grad_in[j];
         } else {
             double gd = 0.0;
-            for (int64_t k = 0; k < a.gparts; ++k) gd += a.gpart[k * a.ld + j];
+            if (a.gp_ldk) {
+                const int64_t pc = j / a.gp_ldk;
+                gd = a.gpart[pc * a.gp_piece_stride + (j - pc * a.gp_ldk)];
+            } else {
+                for (int64_t k = 0; k < a.gparts; ++k) gd += a.gpart[k * a.ld + j];
+            }
             gd = 2.0 * gd;  // potential.py:708  2 * np.dot(Aw.T, r)
             const double dl = reg_delta(a, j);
             double gm = 0.0;

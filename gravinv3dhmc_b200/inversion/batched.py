@@ -203,7 +203,7 @@ class _DrawAhead:
 class HMCBatch:
     def __init__(self, model, nchains, delta, Lrange, initial_model, aprior_model, boundaries,
                  constraint, log_factor, dobs, RegulFactor, regularization, beta, seed, Sigma,
-                 save_folder="mychain", rng="numpy", quiet=False):
+                 save_folder="mychain", rng="numpy", quiet=False, driver="auto"):
         if constraint not in _lib.CONSTRAINTS:
             raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
         if regularization not in _lib.REG_KINDS:
@@ -243,16 +243,26 @@ class HMCBatch:
             x0 = mw
         self.x = np.ascontiguousarray(np.tile(x0, (self.nchains, 1)))
         self.reg = reg_params(regularization, constraint, model.mshape, RegulFactor, beta, log_factor)
-        if getattr(model, "world", 1) > 1:
+        sharded = getattr(model, "world", 1) > 1
+        # row-sharded batches: "device" = the C loop with all-reduce hooks (overlapped, streaming
+        # capable); "host" = the same exchange driven kernel by kernel from Python (_engine.py)
+        # ("device-hooks" forces the hook machinery on an unsharded model: reductions over one rank)
+        if driver == "auto":
+            driver = "device" if getattr(model.Aw_pad, "is_cuda", False) else "host"
+        self._npieces = None
+        if isinstance(driver, tuple):
+            driver, self._npieces = driver
+        if sharded and driver == "host":
             self._sh = _ShardedBatchState(self)
             return
         L = _lib.lib()
         m = model
-        cfg = _lib.HmcConfig(m.n_total, m.M, m.ld, 1 if m.fixed else 0, 0, self.reg)
+        lo, hi = m.rows if sharded else (0, m.n_total)
+        cfg = _lib.HmcConfig(hi - lo, m.M, m.ld, 1 if m.fixed else 0, 0, self.reg)
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        self._host = dict(dobs=f(m.dobs), low=f(self.low), high=f(self.high),
+        self._host = dict(dobs=f(m.dobs[lo:hi]), low=f(self.low), high=f(self.high),
                           apr=f(self.aprior_model), wmsq=f(m.WmSquare.diagonal()))
-        fix = f(m.grav_fix) if m.fixed else None
+        fix = f(np.asarray(m.grav_fix, dtype=np.float64)[lo:hi]) if m.fixed else None
         h = C.c_void_p()
         _lib.check(L.gi_hmcb_create(C.byref(cfg), self.nchains, _lib.ptr(m.Aw_pad),
                                     _lib.ptr(self._host["dobs"]), _lib.ptr(fix),
@@ -260,7 +270,56 @@ class HMCBatch:
                                     _lib.ptr(self._host["apr"]), _lib.ptr(self._host["wmsq"]),
                                     _lib.stream_ptr(), C.byref(h)), "gi_hmcb_create")
         self._h = h
+        if sharded or driver == "device-hooks":
+            self._attach_shard_hooks(lo, hi)
         _lib.check(L.gi_hmcb_set_state(self._h, _lib.ptr(self.x)), "gi_hmcb_set_state")
+
+    def _attach_shard_hooks(self, lo, hi):
+        """row-sharded model: the device loop calls back here at its exchange points and
+        torch.distributed (NCCL) sums over the ranks, ordered on the current stream"""
+        import torch
+        import torch.distributed as dist
+
+        m, L = self.model, _lib.lib()
+        Cp = int(L.gi_hmcb_padded_chains(self._h))
+        ld = m.ld
+        npieces = self._npieces or next(
+            (k for k in (8, 4, 2) if ld % (256 * k) == 0 and ld // k >= 32768), 1)
+        dev = m.Aw_pad.device
+        self._gext = torch.zeros(Cp * ld, dtype=torch.float64, device=dev)
+        self._red = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+        n = Cp * (ld // npieces)
+        pieces = [self._gext[k * n:(k + 1) * n] for k in range(npieces)]
+        red0, red1 = self._red[:Cp], self._red[Cp:]
+        pending, group = [], m.group
+        single = getattr(m, "world", 1) == 1  # one rank: every sum is already complete
+
+        def hook(user, what, piece, async_):
+            try:
+                if single:
+                    return 0
+                if what == 3:
+                    for w in pending:
+                        w.wait()
+                    pending.clear()
+                    return 0
+                t = red0 if what == 0 else red1 if what == 2 else pieces[piece]
+                if async_:
+                    pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True))
+                else:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                return 0
+            except Exception:  # an exception must not unwind through the C frames
+                import traceback
+
+                traceback.print_exc()
+                return -1
+
+        self._hook = _lib.SHARD_HOOK(hook)  # keep the callback object alive with the handle
+        dobs_c = np.ascontiguousarray(m.dobs[lo:hi] - float(np.mean(m.dobs)))
+        _lib.check(L.gi_hmcb_set_shard(self._h, m.n_total, _lib.ptr(dobs_c), _lib.ptr(self._gext),
+                                       npieces, _lib.ptr(self._red), self._hook, None),
+                   "gi_hmcb_set_shard")
 
     def close(self):
         if self._h is not None:
@@ -362,13 +421,14 @@ class HMCBatch:
         so no chain idles while others finish longer trajectories.  Same draws, same decisions and
         same files as `sample()`; single-GPU only."""
         if self._sh is not None:
-            raise NotImplementedError("streaming is a single-GPU mode; use sample() when row-sharded")
+            raise NotImplementedError("streaming needs the device driver (HMCBatch(driver='device'))")
         if self.rng != "numpy":
             raise NotImplementedError("streaming uses the host (reference-order) RNG")
         torch = _lib.require_cuda()
         lib = _lib.lib()
         nc, M = self.nchains, self.model.M
         folders = [self.save_folder + str(c) for c in range(nc)]
+        write = write and getattr(self.model, "rank", 0) == 0  # every rank holds the same chains
         if write:
             for fo in folders:
                 if not os.path.exists(fo):

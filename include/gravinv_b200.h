@@ -275,6 +275,24 @@ int gi_hmcb_propose(gi_hmcb *h, const double *p0_host, const int32_t *L_host, do
 /* device draws: chain c uses the Philox key seed + c (like the reference's seed + myrank) */
 int gi_hmcb_propose_philox(gi_hmcb *h, uint64_t seed, uint64_t counter, double sigma,
                            const int32_t *L_host, double dt, gi_hmc_result *results);
+/* Row-sharded batches (G partitioned by observation rows over GPUs): the handle is created
+ * over this rank's rows (cfg.N = local rows) and told the global row count; at the two exchange
+ * points of every gradient evaluation it calls `hook` on its stream's behalf:
+ *   what 0: sum-reduce red_dev[0 : Cp]      (sum of the forward data per chain -> global mean)
+ *   what 1: sum-reduce gradient piece `piece` (gdata_dev + piece*Cp*(ld/npieces), Cp*(ld/npieces)
+ *           doubles); async != 0: the reduction may complete later, what 3 waits for all of them --
+ *           the adjoint contraction of the next piece overlaps the reduction of the previous one
+ *   what 2: sum-reduce red_dev[Cp : 2*Cp]   (sum of squared residuals per chain)
+ *   what 3: make the handle's stream wait for the outstanding asynchronous reductions
+ * All reductions are in place over every rank and must be ordered after the work already queued on
+ * the handle's stream (torch.distributed with NCCL does exactly this).  gdata_dev ([npieces][Cp]
+ * [ld/npieces], ld/npieces a multiple of 256) and red_dev ([2*Cp]) are caller-owned so the caller's
+ * collective library can address them.  dobs_c_host = this rank's rows of dobs - mean(all dobs).
+ * Every rank must feed identical draws; the replicated chain state then stays bitwise identical. */
+typedef int (*gi_shard_hook)(void *user, int32_t what, int32_t piece, int32_t async);
+int gi_hmcb_set_shard(gi_hmcb *h, int64_t n_total, const double *dobs_c_host, double *gdata_dev,
+                      int32_t npieces, double *red_dev, gi_shard_hook hook, void *user);
+
 /* Streaming mode: every chain runs its own sequence of proposals back to back.  All chains share
  * each gradient evaluation (one "batch step"), and a chain that ends a trajectory -- Metropolis test,
  * commit -- opens its next one inside the same step, so no chain idles while others finish longer

@@ -56,36 +56,55 @@ def main():
         assert [(L, bool(a)) for L, a in ch.proposals] == [(L, bool(a)) for L, a in ref["log"]], reg
         assert np.max(np.abs(ch.x_final - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"])), reg
         assert any(a for _, a in ch.proposals), reg
-    # ---- batch of chains, row-sharded ----
+    # ---- batch of chains, row-sharded: device loop with all-reduce hooks, and the host-driven one ----
     nch, nprops = 5, 5
-    bt = batched.HMCBatch(model, nch, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
-                          "mandatory", 1000, dobs, 1.0, "MS", 0.001, 3, 1.0,
-                          save_folder=os.path.join(tmp, "b%d_" % rank), quiet=True)
-    traces = []
-    for _ in range(nprops):
-        tr = {}
-        bt.propose(trace=tr)
-        traces.append(tr)
     nacc = nrej = 0
-    for c in range(nch):
-        otr = []
-        onp.hmc_sample(om, 10 ** 6, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
-                       "mandatory", 1000, 1.0, "MS", 0.001, 3, 1.0, myrank=c, max_proposals=nprops,
-                       trace=otr)
-        assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(t["L"], bool(t["accept"])) for t in otr]
-        for k, t in enumerate(otr):
-            L = t["L"]
-            rx = np.array([x for x, _ in t["steps"]])
-            rU = np.array([U for _, U in t["steps"]])
-            gx, gU = traces[k]["x"][: L + 1, c], traces[k]["U"][: L + 1, c]
-            assert np.max(np.abs(gx - rx) / np.max(np.abs(rx), axis=1, keepdims=True)) < 1e-9
-            assert np.max(np.abs(gU - rU) / np.abs(rU)) < 1e-9
-            nacc += bool(t["accept"])
-            nrej += not t["accept"]
-    # the replicated state is bitwise identical on every rank
-    xs = [torch.zeros_like(bt._sh.x_cur) for _ in range(world)]
-    dist.all_gather(xs, bt._sh.x_cur)
-    assert all(torch.equal(xs[0], x) for x in xs)
+    finals = {}
+    for driver in ("device", "host"):
+        bt = batched.HMCBatch(model, nch, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                              "mandatory", 1000, dobs, 1.0, "MS", 0.001, 3, 1.0,
+                              save_folder=os.path.join(tmp, "b%s%d_" % (driver, rank)), quiet=True,
+                              driver=driver)
+        assert (bt._sh is None) == (driver == "device")
+        traces = []
+        for _ in range(nprops):
+            tr = {}
+            bt.propose(trace=tr)
+            traces.append(tr)
+        for c in range(nch):
+            otr = []
+            onp.hmc_sample(om, 10 ** 6, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                           "mandatory", 1000, 1.0, "MS", 0.001, 3, 1.0, myrank=c, max_proposals=nprops,
+                           trace=otr)
+            assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(t["L"], bool(t["accept"])) for t in otr]
+            for k, t in enumerate(otr):
+                L = t["L"]
+                rx = np.array([x for x, _ in t["steps"]])
+                rU = np.array([U for _, U in t["steps"]])
+                gx, gU = traces[k]["x"][: L + 1, c], traces[k]["U"][: L + 1, c]
+                assert np.max(np.abs(gx - rx) / np.max(np.abs(rx), axis=1, keepdims=True)) < 1e-9
+                assert np.max(np.abs(gU - rU) / np.abs(rU)) < 1e-9
+                nacc += bool(t["accept"])
+                nrej += not t["accept"]
+        finals[driver] = bt.x.copy()
+        if driver == "device":
+            # the replicated state is bitwise identical on every rank
+            xs = [torch.zeros(nch, M, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(xs, torch.as_tensor(bt.x).cuda())
+            assert all(torch.equal(xs[0], x) for x in xs)
+            bt.close()
+    assert np.allclose(finals["device"], finals["host"], rtol=1e-9, atol=0)
+    # ---- streaming sampler over the row-sharded kernel (device driver), TV on the full grid ----
+    bs = batched.HMCBatch(model, 6, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
+                          "mandatory", 1000, dobs, 0.05, "TV", 0.001, 3, 0.05,
+                          save_folder=os.path.join(tmp, "st%d_" % rank), quiet=True)
+    bs.stream(10 ** 6, 0, max_proposals=4, write=(rank == 0))
+    for c in range(6):
+        ref = onp.hmc_sample(om, 10 ** 6, 0, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
+                             "mandatory", 1000, 0.05, "TV", 0.001, 3, 0.05, myrank=c, max_proposals=4)
+        assert [(L, bool(a)) for L, a in bs.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
+        assert np.max(np.abs(bs.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"]))
+    bs.close()
     dist.barrier()
     if rank == 0:
         print("multi_gpu_check ok: world=%d, %d accepted / %d rejected batch proposals match the oracle"

@@ -249,3 +249,30 @@ def test_batch_philox_reproducible_and_errors(golden, tmp_path):
     with pytest.raises(ValueError, match="regularization"):
         batched.HMCBatch(model, 2, 0.01, [1, 2], np.ones(M), np.ones(M), b, "mandatory", 1000, dobs,
                          1.0, "L1", 0.001, 1, 0.01)
+
+
+@pytest.mark.parametrize("npieces", [1, 2])
+def test_shard_hook_machinery_single_rank(tmp_path, npieces):
+    """the row-sharded device loop (exchange hooks, piece-major adjoint output reduced piece by piece)
+    with ONE rank, where every reduction is the identity: it must reproduce the plain batched chain
+    (to rounding: the centred data come from numpy's mean here and from a long-double mean there;
+    the multi-rank runs are in tests/multi_gpu_check.py)"""
+    rng = np.random.RandomState(4)
+    mesh_range, spacing = (0, 1600, 0, 1600, 0, 200), (100, 100, 100)   # 2 x 16 x 16 = 512 cells
+    xs, ys = np.meshgrid(np.linspace(50, 1550, 7), np.linspace(50, 1550, 6))
+    obs = (xs.ravel(), ys.ravel(), np.full(xs.size, -20.0))
+    model = potential.GravMagModule(rng.standard_normal(xs.size), mesh_range, spacing, obs, verbose=False)
+    M = model.M
+    assert model.ld == 512
+    b = np.zeros((M, 2))
+    b[:, 1] = 1.0
+    out = {}
+    for driver in ("device", ("device-hooks", npieces)):
+        bt = batched.HMCBatch(model, 5, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                              "mandatory", 1000, model.dobs, 0.5, "TV", 0.001, 9, 0.05,
+                              save_folder=str(tmp_path / "h"), quiet=True, driver=driver)
+        bt.stream(10 ** 6, 0, max_proposals=4, write=False)
+        out[driver if isinstance(driver, str) else driver[0]] = (bt.proposals, bt.x.copy())
+        bt.close()
+    assert out["device"][0] == out["device-hooks"][0]
+    assert np.allclose(out["device"][1], out["device-hooks"][1], rtol=1e-10, atol=1e-14)
