@@ -583,11 +583,21 @@ int gi::batched_plan_init(gi_plan *p) {
     p->b_C = 8 * p->b_nt;
     p->b_npad = ceil_div(p->nrows, kAdjK) * kAdjK;
     p->b_rowblocks = ceil_div(p->nrows, kFwdRows);
-    // k-chunks: aim at ~32 waves of one CTA per SM; chunk a multiple of the 32-voxel stage
+    // k-chunks: whole waves of one CTA per SM (every CTA does the same work, so a partial last wave
+    // is pure loss), at least ~8 of them, and as few chunks as that allows -- the partials
+    // [nkc][C][nrows] are re-read by the misfit kernel; chunk a multiple of the 32-voxel stage
     const int sms = sm_count();
-    int64_t nkc = std::max<int64_t>(1, (32LL * sms) / p->b_rowblocks);
-    nkc = std::min<int64_t>(nkc, ceil_div(p->ld, 8 * kFwdK));  // >= 8 stages per CTA
-    nkc = std::max<int64_t>(nkc, 1);
+    const int64_t max_nkc = std::max<int64_t>(1, ceil_div(p->ld, 8 * kFwdK));  // >= 8 stages per CTA
+    int64_t nkc = 1;
+    double best = -1.0;
+    for (int64_t cand = 1; cand <= std::min<int64_t>(max_nkc, 2048); ++cand) {
+        const int64_t tiles = cand * p->b_rowblocks;
+        const int64_t waves = ceil_div(tiles, sms);
+        const double eff = (double)tiles / (double)(waves * sms);  // fill of the last wave
+        // prefer >= 8 waves, then the best fill; ties go to fewer chunks
+        const double score = eff - (waves < 8 ? 0.5 * (8 - waves) / 8.0 : 0.0) - 1e-4 * cand;
+        if (score > best) { best = score; nkc = cand; }
+    }
     p->b_kchunk = ceil_div(ceil_div(p->ld, nkc), kFwdK) * kFwdK;
     p->b_nkc = ceil_div(p->ld, p->b_kchunk);
     p->b_strips = ceil_div(p->ld, kAdjCols);
