@@ -59,6 +59,36 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// ---- mbarrier helpers (per-stage full/empty barriers instead of a CTA-wide __syncthreads) --------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+// arrival that fires once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void mbar_arrive_on_copies(uint64_t *bar) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, int parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+
+#ifndef GI_MBAR
+#define GI_MBAR 1
+#endif
+constexpr int kMbarBytes = 128;  // full[kStages] + empty[kStages] behind the stage ring
+
 constexpr int kGemmThreads = 256;
 #ifndef GI_STAGES
 #define GI_STAGES 4
@@ -70,6 +100,9 @@ constexpr int kGemmThreads = 256;
 #define GI_ADJK 16
 #endif
 constexpr int kStages = GI_STAGES;
+// tiles in flight ahead of the one being consumed (one less with mbarriers: a stage is refilled two
+// iterations after its last read, so a warp never waits for the others)
+constexpr int kPrefetch = GI_MBAR ? kStages - 2 : kStages - 1;
 constexpr int kFwdRows = 128;  // rows per CTA
 constexpr int kFwdK = GI_FWDK;  // voxels per stage (32 or 64)
 constexpr int kAdjCols = 256;  // voxels per CTA
@@ -138,15 +171,30 @@ gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
 #pragma unroll
         for (int j = 0; j < NTW; ++j) acc[rm][j][0] = acc[rm][j][1] = 0.0;
 
+#if GI_MBAR
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * STAGE), *empty = full + kStages;
+    if (tid == 0)
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, T); mbar_init(empty + s, T / 32); }
+    __syncthreads();
+#endif
 #pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) {
-        if (s < ntiles) load_stage(s, s);
+    for (int s = 0; s < kPrefetch; ++s) {
+        if (s < ntiles) {
+            load_stage(s, s);
+#if GI_MBAR
+            mbar_arrive_on_copies(full + s);
+#endif
+        }
         cp_async_commit();
     }
     const int sw = (g & 1) << 2;  // rows 16wr + 8rm + g and chains 8j + g have the parity of g
     for (int kt = 0; kt < ntiles; ++kt) {
+#if GI_MBAR
+        mbar_wait(full + kt % kStages, (kt / kStages) & 1);
+#else
         cp_async_wait<kStages - 2>();
         __syncthreads();
+#endif
         const unsigned char *gs = smem + (kt % kStages) * STAGE;
         const unsigned char *xs = gs + GB + wc * NTW * 8 * PITCH;
 #pragma unroll
@@ -172,12 +220,25 @@ gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
                 }
             }
             if (q == 0) {
-                // refill the stage consumed in the previous iteration; issued behind the first
-                // k-group so the tensor pipe has work while the copies are set up
-                if (kt + kStages - 1 < ntiles) load_stage((kt + kStages - 1) % kStages, kt + kStages - 1);
+                // refill a stage every warp has finished with; issued behind the first k-group
+                // so the tensor pipe has work while the copies are set up
+                const int tl = kt + kPrefetch;
+                if (tl < ntiles) {
+#if GI_MBAR
+                    if (tl >= kStages) mbar_wait(empty + tl % kStages, ((tl - kStages) / kStages) & 1);
+                    load_stage(tl % kStages, tl);
+                    mbar_arrive_on_copies(full + tl % kStages);
+#else
+                    load_stage(tl % kStages, tl);
+#endif
+                }
                 cp_async_commit();
             }
         }
+#if GI_MBAR
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + kt % kStages);
+#endif
     }
     cp_async_wait<0>();
 #pragma unroll
@@ -265,15 +326,30 @@ gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
 #pragma unroll
         for (int j = 0; j < NTW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+#if GI_MBAR
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * STAGE), *empty = full + kStages;
+    if (tid == 0)
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, T); mbar_init(empty + s, T / 32); }
+    __syncthreads();
+#endif
 #pragma unroll
-    for (int s = 0; s < kStages - 1; ++s) {
-        if (s < ntiles) load_stage(s, s);
+    for (int s = 0; s < kPrefetch; ++s) {
+        if (s < ntiles) {
+            load_stage(s, s);
+#if GI_MBAR
+            mbar_arrive_on_copies(full + s);
+#endif
+        }
         cp_async_commit();
     }
     const int a_lo = ((16 * wv + g) ^ (2 * t)) << 4, a_hi = ((16 * wv + 8 + g) ^ (2 * t)) << 4;
     for (int ot = 0; ot < ntiles; ++ot) {
+#if GI_MBAR
+        mbar_wait(full + ot % kStages, (ot / kStages) & 1);
+#else
         cp_async_wait<kStages - 2>();
         __syncthreads();
+#endif
         const unsigned char *gs = smem + (ot % kStages) * STAGE;
         const unsigned char *rs = gs + GB + wc * NTW * 8 * RPITCH;
 #pragma unroll
@@ -290,13 +366,27 @@ gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
                 for (int i = 0; i < 4; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b);
             }
             if (kq == 0) {
-                // refill the stage consumed in the previous iteration (every warp is past the
-                // barrier above, so nobody reads it any more); issued here, behind the first
+                // refill a stage every warp has finished with; issued here, behind the first
                 // k-group, so that the tensor pipe already has work while the copies are set up
-                if (ot + kStages - 1 < ntiles) load_stage((ot + kStages - 1) % kStages, ot + kStages - 1);
+                const int tl = ot + kPrefetch;
+                if (tl < ntiles) {
+#if GI_MBAR
+                    // the stage was last read for tile tl - kStages (two iterations ago): its
+                    // "empty" barrier has long completed unless some warp lags a whole stage
+                    if (tl >= kStages) mbar_wait(empty + tl % kStages, ((tl - kStages) / kStages) & 1);
+                    load_stage(tl % kStages, tl);
+                    mbar_arrive_on_copies(full + tl % kStages);
+#else
+                    load_stage(tl % kStages, tl);
+#endif
+                }
                 cp_async_commit();
             }
         }
+#if GI_MBAR
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + ot % kStages);
+#endif
     }
     cp_async_wait<0>();
 #pragma unroll
@@ -563,16 +653,24 @@ using namespace gi;
 static int pick_nt(int nchains) { return nchains <= 8 ? 1 : nchains <= 16 ? 2 : nchains <= 32 ? 4 : 8; }
 
 // warps along the chain dimension per n-tile count (see gemm_fwd_kernel)
-template <int NT> struct WarpSplit { static constexpr int fwd = NT >= 4 ? 2 : 1, adj = NT >= 4 ? 2 : 1; };
+#ifndef GI_WC_FWD
+#define GI_WC_FWD 2
+#endif
+#ifndef GI_WC_ADJ
+#define GI_WC_ADJ 1
+#endif
+template <int NT> struct WarpSplit {
+    static constexpr int fwd = NT >= 4 ? GI_WC_FWD : 1, adj = NT >= 4 ? GI_WC_ADJ : 1;
+};
 
 template <int NT>
 static int set_smem_attrs() {
     GI_CUDA(cudaFuncSetAttribute(gemm_fwd_kernel<NT, WarpSplit<NT>::fwd>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kStages * fwd_stage_bytes<NT>()));
+                                 kStages * fwd_stage_bytes<NT>() + kMbarBytes));
     GI_CUDA(cudaFuncSetAttribute(gemm_adj_kernel<NT, WarpSplit<NT>::adj>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kStages * adj_stage_bytes<NT>()));
+                                 kStages * adj_stage_bytes<NT>() + kMbarBytes));
     return GI_OK;
 }
 
@@ -629,7 +727,7 @@ int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream
     const unsigned grid = (unsigned)(p->b_nkc * p->b_rowblocks);
 #define GI_FWD(NT)                                                                             \
     gemm_fwd_kernel<NT, WarpSplit<NT>::fwd>                                                    \
-        <<<grid, kGemmThreads * WarpSplit<NT>::fwd, kStages * fwd_stage_bytes<NT>(), s>>>(     \
+        <<<grid, kGemmThreads * WarpSplit<NT>::fwd, kStages * fwd_stage_bytes<NT>() + kMbarBytes, s>>>(     \
         G, p->ld, X, p->nrows, p->b_kchunk, p->b_rowblocks, p->b_part)
     switch (p->b_nt) {
         case 1: GI_FWD(1); break;
@@ -653,7 +751,7 @@ int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *ou
     const int64_t col0 = piece * ldk;
 #define GI_ADJ(NT)                                                                             \
     gemm_adj_kernel<NT, WarpSplit<NT>::adj>                                                    \
-        <<<grid, kGemmThreads * WarpSplit<NT>::adj, kStages * adj_stage_bytes<NT>(), s>>>(     \
+        <<<grid, kGemmThreads * WarpSplit<NT>::adj, kStages * adj_stage_bytes<NT>() + kMbarBytes, s>>>(     \
         G, p->ld, R, p->b_npad, p->nrows, outp, strip0, ldk, col0)
     switch (p->b_nt) {
         case 1: GI_ADJ(1); break;
