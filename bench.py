@@ -37,6 +37,7 @@ WORKLOADS = {
     # name: (nz, ny, nx), cell size [m], observations per side
     "c5": ((64, 128, 128), 100.0, 128),       # BASELINE.json configs[4]
     "c5_half": ((64, 128, 128), 100.0, 90),   # 8100 obs (68 GB) -- for boxes with less free HBM
+    "c5_quarter": ((64, 128, 128), 100.0, 64),  # 4096 obs (34 GB): at 2 GPUs the per-GPU shard of c5 at 8
     "mid": ((32, 64, 64), 100.0, 64),         # 131 072 voxels x 4096 obs (4.3 GB)
     "tiny": ((16, 32, 32), 100.0, 32),        # 16 384 voxels x 1024 obs
 }

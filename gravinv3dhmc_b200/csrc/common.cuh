@@ -45,6 +45,12 @@ __device__ __forceinline__ void ldg4(const double *p, double &a, double &b, doub
                  : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
                  : "l"(p));
 }
+// cache-global variant for buffers that are rewritten in place by the same kernel
+__device__ __forceinline__ void ldg4_cg(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
+                 : "l"(p));
+}
 __device__ __forceinline__ void stg4(double *p, double a, double b, double c, double d) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
                  : "memory");

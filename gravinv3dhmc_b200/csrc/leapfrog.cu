@@ -254,7 +254,7 @@ static int plan_tiles(gi_plan *p) {
     p->adj_rows = ceil_div(p->adj_rows, kAdjUnroll) * kAdjUnroll;
     p->adj_rows = std::min<int64_t>(kAdjMaxRows, p->adj_rows);
     p->adj_nchunks = ceil_div(p->nrows, p->adj_rows);
-    p->upd_blocks = ceil_div(std::max<int64_t>(p->M, 1), kUpdThreads);
+    p->upd_blocks = ceil_div(std::max<int64_t>(p->M, 1), (int64_t)kUpdThreads * kUpdVec * 4);
     return GI_OK;
 }
 

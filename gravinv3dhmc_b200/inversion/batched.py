@@ -287,6 +287,8 @@ class HMCBatch:
         # piece still fills the 148 SMs for ~7 waves (8 pieces: 3.5 waves, 14 % tail loss)
         npieces = self._npieces or next(
             (k for k in (4, 2) if ld % (256 * k) == 0 and ld // k >= 65536), 1)
+        if os.environ.get("GI_NPIECES"):       # diagnostics
+            npieces = int(os.environ["GI_NPIECES"])
         dev = m.Aw_pad.device
         self._gext = torch.zeros(Cp * ld, dtype=torch.float64, device=dev)
         self._red = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
@@ -295,6 +297,9 @@ class HMCBatch:
         red0, red1 = self._red[:Cp], self._red[Cp:]
         pending, group = [], m.group
         single = getattr(m, "world", 1) == 1  # one rank: every sum is already complete
+        if os.environ.get("GI_NULL_HOOK"):     # diagnostics: measure the loop without communication
+            single = True
+
 
         def hook(user, what, piece, async_):
             try:
