@@ -63,6 +63,13 @@ FP64_PEAK_TFLOPS = 37.1
 FP64_PEAK_SRC = "measured here (tools/probes/fp64_peak.cu: DMMA m8n8k4 = DFMA = 37.1 TFLOP/s FP64)"
 
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full`
+# capture of this command at N = 1 (profiles/r01_gemm_c5_ncu_full.txt); algorithmic bytes are
+# 8*N*M = 137.44 GB.  (The same capture's counters of the adjoint kernel overflowed; its traffic at
+# 1/8 of the rows, profiles/r01_gemm_c64_ncu_full_final.txt, is 17.33 GB = 1.009 x algorithmic.)
+NCU_TRAFFIC_BYTES = {("c5", 1, 64, "gemm_fwd"): 138.590020e9 + 0.124359e9}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -507,7 +514,8 @@ def gpu_arm(args):
             "assembly": {"mpairs_per_s": N * M / t_asm / 1e6, "seconds": t_asm,
                          "weighting_seconds": t_wgt},
             "roofline": {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak,
-                         "unit": unit, "frac": achieved / peak, "traffic": None,
+                         "unit": unit, "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, nch, dom)),
                          "peak_source": peak_src, "kernels": kern, "hbm_peak_GBps": hbm_peak},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
