@@ -11,7 +11,7 @@
 // `mpiexec -n 2`), each streaming its own copy of Aw.
 //
 // Layouts: every per-chain vector is chain-major -- X, P, grad: [C][ld]; D: [C][nrows];
-// R: [C][npad] (npad = nrows rounded up to 16, padding zero).  C is padded to 8*NT, NT in {1,2,4,8}.
+// R: [C][npad] (npad = nrows rounded up to 16, padding zero).  C is padded to 8*NT, NT in 1..8.
 //
 // Tiling (B200: 148 SMs, 227 KB smem/CTA, FP64 pipe 37.1 TFLOP/s measured for DFMA and DMMA alike,
 // profiles/r01_fp64_peak_probe.txt -- at C = 64 both passes are FP64-pipe bound, 16 flop/B):
@@ -650,7 +650,7 @@ using namespace gi;
 // =============================================================================================
 // batched plan pieces (declared in plan.cuh, used by gi_plan_* in leapfrog.cu)
 // =============================================================================================
-static int pick_nt(int nchains) { return nchains <= 8 ? 1 : nchains <= 16 ? 2 : nchains <= 32 ? 4 : 8; }
+static int pick_nt(int nchains) { return (nchains + 7) / 8; }  // chains padded to a multiple of 8
 
 // warps along the chain dimension per n-tile count (see gemm_fwd_kernel)
 #ifndef GI_WC_FWD
@@ -660,7 +660,8 @@ static int pick_nt(int nchains) { return nchains <= 8 ? 1 : nchains <= 16 ? 2 : 
 #define GI_WC_ADJ 1
 #endif
 template <int NT> struct WarpSplit {
-    static constexpr int fwd = NT >= 4 ? GI_WC_FWD : 1, adj = NT >= 4 ? GI_WC_ADJ : 1;
+    static constexpr int fwd = (NT >= 4 && NT % 2 == 0) ? GI_WC_FWD : 1;
+    static constexpr int adj = (NT >= 4 && NT % 2 == 0) ? GI_WC_ADJ : 1;
 };
 
 template <int NT>
@@ -711,7 +712,11 @@ int gi::batched_plan_init(gi_plan *p) {
     switch (p->b_nt) {
         case 1: return set_smem_attrs<1>();
         case 2: return set_smem_attrs<2>();
+        case 3: return set_smem_attrs<3>();
         case 4: return set_smem_attrs<4>();
+        case 5: return set_smem_attrs<5>();
+        case 6: return set_smem_attrs<6>();
+        case 7: return set_smem_attrs<7>();
         default: return set_smem_attrs<8>();
     }
 }
@@ -732,7 +737,11 @@ int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream
     switch (p->b_nt) {
         case 1: GI_FWD(1); break;
         case 2: GI_FWD(2); break;
+        case 3: GI_FWD(3); break;
         case 4: GI_FWD(4); break;
+        case 5: GI_FWD(5); break;
+        case 6: GI_FWD(6); break;
+        case 7: GI_FWD(7); break;
         default: GI_FWD(8); break;
     }
 #undef GI_FWD
@@ -756,7 +765,11 @@ int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *ou
     switch (p->b_nt) {
         case 1: GI_ADJ(1); break;
         case 2: GI_ADJ(2); break;
+        case 3: GI_ADJ(3); break;
         case 4: GI_ADJ(4); break;
+        case 5: GI_ADJ(5); break;
+        case 6: GI_ADJ(6); break;
+        case 7: GI_ADJ(7); break;
         default: GI_ADJ(8); break;
     }
 #undef GI_ADJ

@@ -29,7 +29,7 @@ class FakeLib:
 
     def gi_plan_create(self, nrows, M, ld, nchains, out):
         hid = len(self.plans) + 1
-        cp = 1 if nchains == 1 else (8 if nchains <= 8 else 16 if nchains <= 16 else 32 if nchains <= 32 else 64)
+        cp = 1 if nchains == 1 else (int(nchains) + 7) // 8 * 8
         self.plans[hid] = dict(n=int(nrows), M=int(M), ld=int(ld), C=int(nchains), Cp=cp,
                                npad=(int(nrows) + 15) // 16 * 16)
         out._obj.value = hid

@@ -22,7 +22,8 @@ def normwise(a, b):
 
 
 @pytest.mark.parametrize("n,m,c", [(1, 1, 2), (5, 40, 3), (17, 300, 8), (130, 1000, 9), (257, 2100, 16),
-                                   (600, 6000, 33), (1000, 5003, 64), (2049, 4100, 64)])
+                                   (600, 6000, 33), (1000, 5003, 64), (2049, 4100, 64), (300, 2000, 20), (300, 2000, 48),
+                                   (300, 2000, 51)])
 def test_gemm_fwd_adj_vs_numpy(n, m, c):
     L = _lib.lib()
     rng = np.random.RandomState(n + 3 * m + c)
