@@ -903,6 +903,9 @@ struct gi_hmcb {
     gi_stream_record *rec_dev, *rec_host;
     int64_t rec_cap;
     double *s_xin, *s_xout, *s_mwin, *s_mwout;
+    cudaStream_t copy_stream;        // device->host copies of the per-record positions
+    cudaEvent_t ev_commit, ev_copied;
+    bool copies_pending;
     // row-sharded mode (gi_hmcb_set_shard)
     int64_t n_total;
     gi_shard_hook hook;
@@ -922,6 +925,9 @@ static void hmcb_free(gi_hmcb *h) {
     cudaFree(h->st);
     cudaFree(h->qp);
     cudaFree(h->rec_dev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ev_commit) cudaEventDestroy(h->ev_commit);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->rec_host) cudaFreeHost(h->rec_host);
     if (h->st_host) cudaFreeHost(h->st_host);
     gi_plan_destroy(h->plan);
@@ -1325,6 +1331,12 @@ extern "C" int gi_hmcb_stream_begin(gi_hmcb *h, double dt) {
         GI_CUDA(cudaMalloc(&h->rec_dev, sizeof(gi_stream_record) * h->rec_cap));
         GI_CUDA(cudaMallocHost(&h->rec_host, sizeof(gi_stream_record) * h->rec_cap));
     }
+    if (!h->copy_stream) {
+        GI_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        GI_CUDA(cudaEventCreateWithFlags(&h->ev_commit, cudaEventDisableTiming));
+        GI_CUDA(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+    }
+    h->copies_pending = false;
     memset(h->cq, 0, sizeof(h->cq));
     h->streaming = true;
     h->stream_dt = dt;
@@ -1332,9 +1344,9 @@ extern "C" int gi_hmcb_stream_begin(gi_hmcb *h, double dt) {
     return GI_OK;
 }
 
-extern "C" int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u,
-                                   const double *p0_host) {
-    GI_REQUIRE(h && h->streaming && p0_host, "gi_hmcb_stream_feed: call gi_hmcb_stream_begin first");
+static int stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u, const double *p0,
+                       cudaMemcpyKind kind) {
+    GI_REQUIRE(h && h->streaming && p0, "gi_hmcb_stream_feed: call gi_hmcb_stream_begin first");
     GI_REQUIRE(chain >= 0 && chain < h->nchains && L >= 1, "gi_hmcb_stream_feed: bad chain or L");
     gi_hmcb::ChainQ &q = h->cq[chain];
     if (q.qn >= 2) {
@@ -1343,12 +1355,22 @@ extern "C" int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double 
     }
     const int slot = (q.qhead + q.qn) & 1;
     // same stream as the kernels: the copy is ordered after the step that consumed this slot
-    GI_CUDA(cudaMemcpyAsync(h->qp + ((int64_t)slot * h->C + chain) * h->cfg.ld, p0_host,
-                            sizeof(double) * h->cfg.M, cudaMemcpyHostToDevice, h->stream));
+    GI_CUDA(cudaMemcpyAsync(h->qp + ((int64_t)slot * h->C + chain) * h->cfg.ld, p0,
+                            sizeof(double) * h->cfg.M, kind, h->stream));
     q.qL[slot] = L;
     q.qu[slot] = u;
     q.qn += 1;
     return GI_OK;
+}
+
+extern "C" int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u,
+                                   const double *p0_host) {
+    return stream_feed(h, chain, L, u, p0_host, cudaMemcpyHostToDevice);
+}
+
+extern "C" int gi_hmcb_stream_feed_dev(gi_hmcb *h, int32_t chain, int32_t L, double u,
+                                       const double *p0_dev) {
+    return stream_feed(h, chain, L, u, p0_dev, cudaMemcpyDeviceToDevice);
 }
 
 extern "C" int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps) {
@@ -1461,15 +1483,24 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         if (any_fin) {
             const int64_t n = std::max(M, N);
             dim3 grid((unsigned)ceil_div(n, 256), (unsigned)C);
+            // x_cur is about to change: the positions still being copied out must be gone first
+            if (h->copies_pending) GI_CUDA(cudaStreamWaitEvent(s, h->ev_copied, 0));
             commit_stream_kernel<<<grid, 256, 0, s>>>(h->st, sc, M, N, ld, h->s_xin, h->s_mwin, h->gnew,
                                                       h->d, h->x_cur, h->mw_cur, h->g_cur, h->d_cur);
             GI_LAUNCH_CHECK();
             h->launches += 1;
-            if (x_host)
+            if (x_host) {
+                // the copies run on their own stream, under the next steps' contractions
+                GI_CUDA(cudaEventRecord(h->ev_commit, s));
+                GI_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_commit, 0));
                 for (int c = 0; c < h->nchains; ++c)
                     if (sc.fin[c])
                         GI_CUDA(cudaMemcpyAsync(x_host + (int64_t)sc.rec[c] * M, h->x_cur + c * ld,
-                                                sizeof(double) * M, cudaMemcpyDeviceToHost, s));
+                                                sizeof(double) * M, cudaMemcpyDeviceToHost,
+                                                h->copy_stream));
+                GI_CUDA(cudaEventRecord(h->ev_copied, h->copy_stream));
+                h->copies_pending = true;
+            }
         }
         if (any_start) {
             // opening half step of the next trajectory from the (possibly just committed) state
@@ -1509,6 +1540,10 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         delete[] tmp;
     } else {
         GI_CUDA(cudaStreamSynchronize(s));
+    }
+    if (h->copies_pending) {
+        GI_CUDA(cudaStreamSynchronize(h->copy_stream));
+        h->copies_pending = false;
     }
     *nrecords = nrec;
     if (steps_done) *steps_done = done;

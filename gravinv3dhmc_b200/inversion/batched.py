@@ -142,10 +142,12 @@ class _DrawAhead:
     threads while the GPU runs (numpy's generators and the ctypes calls both release the GIL).
     Chain c is served by worker c % nworkers, so every chain's stream is consumed sequentially."""
 
-    def __init__(self, streams, Lrange, M, Sigma, depth=2, nworkers=None):
+    def __init__(self, streams, Lrange, M, Sigma, depth=2, nworkers=None, owned=None):
         self.streams, self.Lrange, self.M, self.Sigma, self.depth = streams, Lrange, M, Sigma, depth
         self.ready = [collections.deque() for _ in streams]
-        self.enabled = [True] * len(streams)
+        # row-sharded runs: every rank needs the same draws, so chain c is drawn by rank c % world
+        # only and broadcast (`owned[c]` False = another rank's chain)
+        self.enabled = [True] * len(streams) if owned is None else list(owned)
         self.cv = threading.Condition()
         self.stop_flag = False
         n = nworkers or max(1, min(8, (os.cpu_count() or 2) // 2, len(streams)))
@@ -406,12 +408,37 @@ class HMCBatch:
     def start_draws(self, wait=False):
         """start preparing the draws of the next proposals on background threads (optional; `stream`
         does it itself).  `wait=True` returns once two proposals per chain are ready."""
-        self._ahead = _DrawAhead(self.streams, self.Lrange, self.model.M, self.Sigma)
+        world, rank = getattr(self.model, "world", 1), getattr(self.model, "rank", 0)
+        self._owner = [c % world for c in range(self.nchains)]
+        owned = [o == rank for o in self._owner] if (world > 1 and self._sh is None) else None
+        self._ahead = _DrawAhead(self.streams, self.Lrange, self.model.M, self.Sigma, owned=owned)
         self._ahead.start()
         self._stream_buffers()
         if wait:
             self._ahead.wait_primed()
         return self._ahead
+
+    def _broadcast_draw(self, ahead, c, rank):
+        """row-sharded streaming: the owner rank of chain c (c % world) draws (L, p0, u) from the
+        chain's RandomState(seed + c) and broadcasts them over NCCL; returns (L, u, p0 on device)"""
+        import torch
+        import torch.distributed as dist
+
+        M, dev = self.model.M, self.model.Aw_pad.device
+        if getattr(self, "_bc", None) is None:
+            self._bc = [torch.zeros(M + 2, dtype=torch.float64, device=dev) for _ in range(4)]
+            self._bc_host = torch.zeros(M + 2, dtype=torch.float64).pin_memory()
+            self._bc_i = 0
+        buf = self._bc[self._bc_i % 4]       # the device copy out of it is queued before reuse
+        self._bc_i += 1
+        if self._owner[c] == rank:
+            L, p0, u = ahead.take(c)
+            h = self._bc_host.numpy()
+            h[:M], h[M], h[M + 1] = p0, L, u
+            buf.copy_(self._bc_host, non_blocking=True)
+        dist.broadcast(buf, src=self._owner[c], group=self.model.group)
+        Lu = buf[M:].cpu().numpy()           # 16 bytes; also orders the pinned staging buffer
+        return int(Lu[0]), float(Lu[1]), buf[:M]
 
     def _stream_buffers(self):
         """record array + pinned staging for the positions that come back with every record"""
@@ -434,8 +461,9 @@ class HMCBatch:
         torch = _lib.require_cuda()
         lib = _lib.lib()
         nc, M = self.nchains, self.model.M
+        world, rank = getattr(self.model, "world", 1), getattr(self.model, "rank", 0)
         folders = [self.save_folder + str(c) for c in range(nc)]
-        write = write and getattr(self.model, "rank", 0) == 0  # every rank holds the same chains
+        write = write and rank == 0  # every rank holds the same chains
         if write:
             for fo in folders:
                 if not os.path.exists(fo):
@@ -457,9 +485,14 @@ class HMCBatch:
             while True:
                 for c in range(nc):
                     while live[c] and inflight[c] < 2 and (max_proposals is None or fed[c] < max_proposals):
-                        L, p0, u = ahead.take(c)
-                        _lib.check(lib.gi_hmcb_stream_feed(self._h, c, L, u, _lib.ptr(p0)),
-                                   "gi_hmcb_stream_feed")
+                        if world > 1:
+                            L, u, p0d = self._broadcast_draw(ahead, c, rank)
+                            _lib.check(lib.gi_hmcb_stream_feed_dev(self._h, c, L, u, _lib.ptr(p0d)),
+                                       "gi_hmcb_stream_feed_dev")
+                        else:
+                            L, p0, u = ahead.take(c)
+                            _lib.check(lib.gi_hmcb_stream_feed(self._h, c, L, u, _lib.ptr(p0)),
+                                       "gi_hmcb_stream_feed")
                         inflight[c] += 1
                         fed[c] += 1
                 run = C.c_int32()

@@ -314,6 +314,8 @@ typedef struct {
 } gi_stream_record;
 int gi_hmcb_stream_begin(gi_hmcb *h, double dt);
 int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u, const double *p0_host);
+/* same as feed with the momentum draw already on the device (e.g. received by a broadcast) */
+int gi_hmcb_stream_feed_dev(gi_hmcb *h, int32_t chain, int32_t L, double u, const double *p0_dev);
 int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps);
 int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records, int32_t max_records,
                            int32_t *nrecords, int32_t *steps_done, double *x_host);
