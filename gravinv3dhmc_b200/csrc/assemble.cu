@@ -198,87 +198,131 @@ struct TessCell {
     double w, e, s, n, top, bottom;
 };
 
-__device__ __forceinline__ double tess_leaf(double lon, double coslat, double sinlat, double radius,
-                                            const TessCell &c) {
-    // scale_nodes (_tesseroid_numba.py:75-91) + kernelz (:207-222)
+// Everything that depends on the cell only is separated from the per-observation part, so that
+// the thread owning a column evaluates it once and reuses it for all its observation rows (the
+// values and the operation order per pair are unchanged -> same bits).
+struct TessLeafC {
+    double lonc[2], sinlatc[2], coslatc[2], rc[2], rck2[2], kappa[2][2], scale;
+};
+
+__device__ __forceinline__ void tess_leaf_consts(const TessCell &c, TessLeafC &L) {
+    // scale_nodes (_tesseroid_numba.py:75-91) + the cell-only factors of kernelz (:207-222)
     const double d2r = kNpPi / 180;
     const double dlon = __dmul_rn(d2r, __dsub_rn(c.e, c.w));
     const double dlat = __dmul_rn(d2r, __dsub_rn(c.n, c.s));
     const double dr = __dsub_rn(c.top, c.bottom);
     const double nodes[2] = {kNodeLo, kNodeHi};
-    double lonc[2], sinlatc[2], coslatc[2], rc[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        lonc[i] = __dadd_rn(__dmul_rn(__dmul_rn(0.5, dlon), nodes[i]),
-                            __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.e, c.w)));
+        L.lonc[i] = __dadd_rn(__dmul_rn(__dmul_rn(0.5, dlon), nodes[i]),
+                              __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.e, c.w)));
         const double latc = __dadd_rn(__dmul_rn(__dmul_rn(0.5, dlat), nodes[i]),
                                       __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.n, c.s)));
-        sinlatc[i] = sin(latc);
-        coslatc[i] = cos(latc);
-        rc[i] = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(0.5, dr), nodes[i]),
-                                    __dmul_rn(0.5, __dadd_rn(c.top, c.bottom))),
-                          kEarthRadius);
+        L.sinlatc[i] = sin(latc);
+        L.coslatc[i] = cos(latc);
+        L.rc[i] = __dadd_rn(__dadd_rn(__dmul_rn(__dmul_rn(0.5, dr), nodes[i]),
+                                      __dmul_rn(0.5, __dadd_rn(c.top, c.bottom))),
+                            kEarthRadius);
     }
-    const double scale = __dmul_rn(__dmul_rn(__dmul_rn(dlon, dlat), dr), 0.125);
+    L.scale = __dmul_rn(__dmul_rn(__dmul_rn(dlon, dlat), dr), 0.125);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) L.rck2[k] = __dmul_rn(L.rc[k], L.rc[k]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) L.kappa[j][k] = __dmul_rn(L.rck2[k], L.coslatc[j]);
+}
+
+__device__ __forceinline__ double tess_leaf_eval(double lon, double coslat, double sinlat, double radius,
+                                                 const TessLeafC &L) {
     const double r_sqr = __dmul_rn(radius, radius);
     double result = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const double coslon = cos(__dsub_rn(lon, lonc[i]));
+        const double coslon = cos(__dsub_rn(lon, L.lonc[i]));
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const double cospsi = __dadd_rn(__dmul_rn(sinlat, sinlatc[j]),
-                                            __dmul_rn(__dmul_rn(coslat, coslatc[j]), coslon));
+            const double cospsi = __dadd_rn(__dmul_rn(sinlat, L.sinlatc[j]),
+                                            __dmul_rn(__dmul_rn(coslat, L.coslatc[j]), coslon));
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const double rck2 = __dmul_rn(rc[k], rc[k]);
                 const double l_sqr = __dsub_rn(
-                    __dadd_rn(r_sqr, rck2), __dmul_rn(__dmul_rn(__dmul_rn(2.0, radius), rc[k]), cospsi));
-                const double kappa = __dmul_rn(rck2, coslatc[j]);
-                const double num = __dmul_rn(kappa, __dsub_rn(__dmul_rn(rc[k], cospsi), radius));
+                    __dadd_rn(r_sqr, L.rck2[k]),
+                    __dmul_rn(__dmul_rn(__dmul_rn(2.0, radius), L.rc[k]), cospsi));
+                const double num = __dmul_rn(L.kappa[j][k], __dsub_rn(__dmul_rn(L.rc[k], cospsi), radius));
                 // l_sqr**1.5 ; pow(x, 1.5) == x*sqrt(x) to within 1 ulp
                 result = __dadd_rn(result, __ddiv_rn(num, __dmul_rn(l_sqr, __dsqrt_rn(l_sqr))));
             }
         }
     }
-    return __dmul_rn(scale, -result);
+    return __dmul_rn(L.scale, -result);
 }
 
-// Decide the split of one cell (distance_size :94-111 + divisions :135-157).
-// Returns nlon | nlat<<2 | nr<<4, err in *err (0 or -1).
-__device__ __forceinline__ int tess_divisions(double lon, double coslat, double sinlat, double radius,
-                                              const TessCell &c, double ratio, int *err) {
+__device__ __forceinline__ double tess_leaf(double lon, double coslat, double sinlat, double radius,
+                                            const TessCell &c) {
+    TessLeafC L;
+    tess_leaf_consts(c, L);
+    return tess_leaf_eval(lon, coslat, sinlat, radius, L);
+}
+
+// Split decision of one cell (distance_size :94-111 + divisions :135-157), cell-only part
+struct TessDivC {
+    double rt2, rt, lont, sinlatt, coslatt, rLlon, rLlat, rLr;
+    bool lon_small, lat_small, r_small;
+};
+
+__device__ __forceinline__ void tess_div_consts(const TessCell &c, double ratio, TessDivC &D) {
     const double d2r = kNpPi / 180;
-    const double rt = __dadd_rn(__dmul_rn(0.5, __dadd_rn(c.top, c.bottom)), kEarthRadius);
-    const double lont = __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.w, c.e));
+    D.rt = __dadd_rn(__dmul_rn(0.5, __dadd_rn(c.top, c.bottom)), kEarthRadius);
+    D.rt2 = __dmul_rn(D.rt, D.rt);
+    D.lont = __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.w, c.e));
     const double latt = __dmul_rn(__dmul_rn(d2r, 0.5), __dadd_rn(c.s, c.n));
-    const double sinlatt = sin(latt), coslatt = cos(latt);
-    const double cospsi = __dadd_rn(__dmul_rn(sinlat, sinlatt),
-                                    __dmul_rn(__dmul_rn(coslat, coslatt), cos(__dsub_rn(lon, lont))));
-    const double distance = __dsqrt_rn(
-        __dsub_rn(__dadd_rn(__dmul_rn(radius, radius), __dmul_rn(rt, rt)),
-                  __dmul_rn(__dmul_rn(__dmul_rn(2.0, radius), rt), cospsi)));
+    D.sinlatt = sin(latt);
+    D.coslatt = cos(latt);
     const double rtop = __dadd_rn(c.top, kEarthRadius);
     const double Llon = __dmul_rn(
-        rtop, acos(__dadd_rn(__dmul_rn(sinlatt, sinlatt),
-                             __dmul_rn(__dmul_rn(coslatt, coslatt),
+        rtop, acos(__dadd_rn(__dmul_rn(D.sinlatt, D.sinlatt),
+                             __dmul_rn(__dmul_rn(D.coslatt, D.coslatt),
                                        cos(__dmul_rn(d2r, __dsub_rn(c.e, c.w)))))));
     const double dn = __dmul_rn(d2r, c.n), ds = __dmul_rn(d2r, c.s);
     const double Llat = __dmul_rn(
         rtop, acos(__dadd_rn(__dmul_rn(sin(dn), sin(ds)), __dmul_rn(cos(dn), cos(ds)))));
     const double Lr = __dsub_rn(c.top, c.bottom);
+    D.rLlon = __dmul_rn(ratio, Llon);
+    D.rLlat = __dmul_rn(ratio, Llat);
+    D.rLr = __dmul_rn(ratio, Lr);
+    D.lon_small = Llon <= 0.1;
+    D.lat_small = Llat <= 0.1;
+    D.r_small = Lr <= 1e3;
+}
+
+// Returns nlon | nlat<<2 | nr<<4, err in *err (0 or -1).
+__device__ __forceinline__ int tess_div_eval(double lon, double coslat, double sinlat, double radius,
+                                             const TessDivC &D, int *err) {
+    const double cospsi = __dadd_rn(__dmul_rn(sinlat, D.sinlatt),
+                                    __dmul_rn(__dmul_rn(coslat, D.coslatt), cos(__dsub_rn(lon, D.lont))));
+    const double distance = __dsqrt_rn(
+        __dsub_rn(__dadd_rn(__dmul_rn(radius, radius), D.rt2),
+                  __dmul_rn(__dmul_rn(__dmul_rn(2.0, radius), D.rt), cospsi)));
     int nlon = 1, nlat = 1, nr = 1, e = 0;
-    if (distance <= __dmul_rn(ratio, Llon)) {
-        if (Llon <= 0.1) e = -1; else nlon = 2;
+    if (distance <= D.rLlon) {
+        if (D.lon_small) e = -1; else nlon = 2;
     }
-    if (distance <= __dmul_rn(ratio, Llat)) {
-        if (Llat <= 0.1) e = -1; else nlat = 2;
+    if (distance <= D.rLlat) {
+        if (D.lat_small) e = -1; else nlat = 2;
     }
-    if (distance <= __dmul_rn(ratio, Lr)) {
-        if (Lr <= 1e3) e = -1; else nr = 2;
+    if (distance <= D.rLr) {
+        if (D.r_small) e = -1; else nr = 2;
     }
     *err = e;
     return nlon | (nlat << 2) | (nr << 4);
+}
+
+__device__ __forceinline__ int tess_divisions(double lon, double coslat, double sinlat, double radius,
+                                              const TessCell &c, double ratio, int *err) {
+    TessDivC D;
+    tess_div_consts(c, ratio, D);
+    return tess_div_eval(lon, coslat, sinlat, radius, D, err);
 }
 
 constexpr int kTessThreads = 128;
@@ -302,17 +346,24 @@ tess_gz_kernel(const double *__restrict__ lon, const double *__restrict__ sinlat
     TessCell stack[kStackSize];  // local memory; only touched when a cell subdivides
     int errsum = 0;
     bool overflow = false;
+    // cell-only parts of the split test and of the quadrature of the un-split cell: once per thread
+    TessDivC rootD;
+    TessLeafC rootL;
+    if (live) {
+        tess_div_consts(root, ratio, rootD);
+        tess_leaf_consts(root, rootL);
+    }
     for (int64_t row = blockIdx.y; row < nrows; row += gridDim.y) {
         double acc = 0.0;
         if (live) {
             const double olon = __ldg(lon + row), osin = __ldg(sinlat + row),
                          ocos = __ldg(coslat + row), orad = __ldg(radius + row);
             int err;
-            const int div0 = tess_divisions(olon, ocos, osin, orad, root, ratio, &err);
+            const int div0 = tess_div_eval(olon, ocos, osin, orad, rootD, &err);
             errsum += err;
             if (div0 == (1 | (1 << 2) | (1 << 4))) {
                 // fast path: no subdivision
-                acc = COUNT ? 1.0 : tess_leaf(olon, ocos, osin, orad, root);
+                acc = COUNT ? 1.0 : tess_leaf_eval(olon, ocos, osin, orad, rootL);
             } else {
                 // engine (_tesseroid_numba.py:32-71): LIFO stack, children pushed lon-major
                 int top = -1;
@@ -450,6 +501,15 @@ extern "C" int gi_prism_gz_assemble(const double *xp, const double *yp, const do
     return GI_OK;
 }
 
+// rows are strided over gridDim.y CTAs: enough CTAs for ~16 waves of 8 CTAs per SM, so that each
+// thread keeps its cell constants for as many observation rows as possible
+static unsigned tess_row_split(int64_t ld, int64_t nrows) {
+    const int64_t xblocks = ceil_div(ld, kTessThreads);
+    int64_t y = (16LL * 8 * sm_count()) / xblocks + 1;
+    y = std::max<int64_t>(1, std::min<int64_t>(y, std::min<int64_t>(nrows, 65535)));
+    return (unsigned)y;
+}
+
 extern "C" int gi_prism_gz_assemble_grid(const double *xp, const double *yp, const double *zp,
                                          int64_t nrows, const double *xn, const double *yn,
                                          const double *zn, int32_t nx, int32_t ny, int32_t nz,
@@ -488,7 +548,7 @@ extern "C" int gi_tess_gz_assemble(const double *lon, const double *sinlat, cons
     if (nrows == 0 || ld == 0) return GI_OK;
     GI_REQUIRE(lon && sinlat && coslat && radius && G && status && (bounds || M == 0),
                "gi_tess_gz_assemble: null pointer");
-    dim3 grid((unsigned)ceil_div(ld, kTessThreads), (unsigned)min((int64_t)65535, nrows));
+    dim3 grid((unsigned)ceil_div(ld, kTessThreads), tess_row_split(ld, nrows));
     tess_gz_kernel<false><<<grid, kTessThreads, 0, (cudaStream_t)stream>>>(
         lon, sinlat, coslat, radius, nrows, bounds, M, ratio, scale1, scale2, G, ld, status);
     GI_LAUNCH_CHECK();
@@ -504,7 +564,7 @@ extern "C" int gi_tess_gz_leafcount(const double *lon, const double *sinlat, con
     if (nrows == 0 || ld == 0) return GI_OK;
     GI_REQUIRE(lon && sinlat && coslat && radius && leaves && status && (bounds || M == 0),
                "gi_tess_gz_leafcount: null pointer");
-    dim3 grid((unsigned)ceil_div(ld, kTessThreads), (unsigned)min((int64_t)65535, nrows));
+    dim3 grid((unsigned)ceil_div(ld, kTessThreads), tess_row_split(ld, nrows));
     tess_gz_kernel<true><<<grid, kTessThreads, 0, (cudaStream_t)stream>>>(
         lon, sinlat, coslat, radius, nrows, bounds, M, ratio, 1.0, 1.0, leaves, ld, status);
     GI_LAUNCH_CHECK();
