@@ -132,7 +132,7 @@ _CPU_SHARED = {}  # the row sample, inherited by the forked chain workers (never
 
 
 def _cpu_worker(args):
-    steps, seed = args
+    steps, seed, warm = args
     Aw, wm, dobs, mshape = (_CPU_SHARED[k] for k in ("Aw", "wm", "dobs", "mshape"))
     try:
         from threadpoolctl import threadpool_limits
@@ -146,13 +146,16 @@ def _cpu_worker(args):
     low, high = wm * HMC["rhomin"], wm * HMC["rhomax"]
     x0 = wm * HMC["init"]
     p0 = rs.randn(M) * HMC["Sigma"]
+    if warm:  # untimed warm-up trajectory (page cache, BLAS buffers)
+        onp.leapfrog(model, x0, HMC["delta"], warm, HMC["RegulFactor"], p0, 0.5, x0, low, high,
+                     "mandatory", 1000, HMC["regularization"], HMC["beta"])
     t0 = time.perf_counter()
     onp.leapfrog(model, x0, HMC["delta"], steps, HMC["RegulFactor"], p0, 0.5, x0, low, high,
                  "mandatory", 1000, HMC["regularization"], HMC["beta"])
     return steps, time.perf_counter() - t0
 
 
-def cpu_reference_arm(workload, sample_rows, steps, cores=None):
+def cpu_reference_arm(workload, sample_rows, steps, cores=None, warm=0):
     """returns dict(value=steps/s scaled to the full row count, ...) for the oracle port."""
     from oracle import oracle_np as onp
     import multiprocessing as mp
@@ -173,7 +176,7 @@ def cpu_reference_arm(workload, sample_rows, steps, cores=None):
     A *= (1.0 / wm)[None, :]
     dobs = A @ (wm * rho)
     _CPU_SHARED.update(Aw=A, wm=wm, dobs=dobs, mshape=mesh.shape)
-    jobs = [(steps, 100 + c) for c in range(cores)]
+    jobs = [(steps, 100 + c, warm) for c in range(cores)]
     ctx = mp.get_context("fork")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -220,21 +223,31 @@ def gpu_arm(args):
               file=sys.stderr)
     lib = _lib.lib()
 
-    mrange, mspacing, obs, rho = workload_geometry(args.workload)
-    N = obs[0].size
-    nz, ny, nx = WORKLOADS[args.workload][0]
-    M = nz * ny * nx
-
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    # ---- setup: assemble this rank's rows, weight in place (timed for the Mpairs/s line) ----
+    # ---- workload: the named one, or -- if this rank's shard plus ~8 GB of chain state does not fit
+    # the free HBM -- the next smaller rung (said in config.workload; every rank decides alike) ----
     free, total = torch.cuda.mem_get_info()
-    lo, hi = potential.split_rows(N, world)[rank]
-    need = (hi - lo) * _lib.padded_ld(M) * 8
-    if need > free - (3 << 30):
-        raise SystemExit("bench.py: shard needs %.1f GB, only %.1f GB free on %s"
-                         % (need / 1e9, free / 1e9, torch.cuda.get_device_name(dev)))
+    ladder = [args.workload] + [w for w in ("c5_half", "c5_quarter", "mid") if w != args.workload]
+    fallback_note = ""
+    for wl in ladder:
+        (nz, ny, nx), _, side = WORKLOADS[wl]
+        N, M = side * side, nz * ny * nx
+        lo, hi = potential.split_rows(N, world)[rank]
+        need = (hi - lo) * _lib.padded_ld(M) * 8 + 12 * _lib.padded_ld(M) * 8 * max(args.chains, 8)
+        fits = torch.tensor([1.0 if need < free - (2 << 30) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)
+        if float(fits[0]) > 0:
+            break
+    else:
+        raise SystemExit("bench.py: not even the smallest workload fits: %.1f GB free on %s"
+                         % (free / 1e9, torch.cuda.get_device_name(dev)))
+    if wl != args.workload:
+        fallback_note = " [%s did not fit the %.0f GB free HBM, ran %s]" % (args.workload, free / 1e9, wl)
+        args.workload = wl
+    mrange, mspacing, obs, rho = workload_geometry(args.workload)
     e0, e1 = ev(), ev()
     torch.cuda.synchronize()
     e0.record()
@@ -503,10 +516,10 @@ def gpu_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, FP64 Aw "
+            "config": {"workload": "%s%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, FP64 Aw "
                                    "%.1f GB row-sharded over %d GPU(s), Damping, %d chain(s) batched as columns; inputs "
                                    "(%.1f GB per GPU per pass) exceed the 126 MB L2, no flush needed"
-                                   % (args.workload, nz, ny, nx, M, N, 8e-9 * N * M, world, nch,
+                                   % (args.workload, fallback_note, nz, ny, nx, M, N, 8e-9 * N * M, world, nch,
                                       8e-9 * n_local * M),
                        "voxels": M, "observations": N, "chains": nch, "parallelism": "rows%d" % world},
             "batch_steps_per_s": steps_per_s / nch,
@@ -534,12 +547,10 @@ def reference_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     (nz, ny, nx), _, side = WORKLOADS[args.workload]
     M, N = nz * ny * nx, side * side
-    steps = max(args.steps, 1)
-    best = None
-    for _ in range(max(1, min(args.warmup, 1))):  # one untimed pass warms the page cache / BLAS
-        pass
-    cpu = cpu_reference_arm(args.workload, args.cpu_rows, min(steps, args.cpu_steps))
-    best = cpu
+    # K timed leapfrog steps per chain after W untimed ones, on the bounded row sample (capped so
+    # the run stays within a few minutes on any host)
+    steps, warm = max(1, min(args.steps, 100)), max(0, min(args.warmup, 5))
+    best = cpu_reference_arm(args.workload, args.cpu_rows, steps, warm=warm)
     v = best["value"]
     return {"impl": "reference", "metric": "hmc_leapfrog_steps_per_s", "value": v,
             "unit": "leapfrog steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
