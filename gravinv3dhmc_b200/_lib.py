@@ -45,6 +45,14 @@ class HmcResult(C.Structure):
                 ("Unew", C.c_double), ("Unew_data", C.c_double), ("Unew_model", C.c_double)]
 
 
+class CgConfig(C.Structure):
+    _fields_ = [("N", C.c_int64), ("M", C.c_int64), ("ld", C.c_int64), ("ncols", C.c_int32),
+                ("variant", C.c_int32), ("reg", RegParams), ("q", C.c_double), ("stop_tol", C.c_double),
+                ("rhomin", C.c_double), ("rhomax", C.c_double)]
+
+
+CG_REGINV, CG_BOOTSTRAP = 0, 1
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _D = C.c_double
@@ -121,6 +129,11 @@ SIGNATURES = {
     "gi_csr_fill": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _P, _P, _P]),
     "gi_hmc_set_wavelet": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _I64]),
     "gi_csr_spmv": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
+    "gi_cg_create": (C.c_int, [C.POINTER(CgConfig), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "gi_cg_destroy": (C.c_int, [_P]),
+    "gi_cg_run": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
+    "gi_cg_get_result": (C.c_int, [_P, _P, _P, _P]),
+    "gi_cg_launch_count": (_I64, [_P]),
 }
 
 SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)

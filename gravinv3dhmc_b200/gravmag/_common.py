@@ -69,3 +69,24 @@ def matvec_padded(Gpad, M, vec, torch):
     finally:
         L.gi_plan_destroy(plan)
     return d
+
+
+def rmatvec_padded(Gpad, M, vec, torch):
+    """result = G[:, :M].T @ vec through the library's deterministic adjoint kernel."""
+    L = _lib.lib()
+    N, ld = Gpad.shape
+    r = torch.as_tensor(vec, dtype=torch.float64, device=Gpad.device).contiguous()
+    g = torch.zeros(ld, dtype=torch.float64, device=Gpad.device)
+    if N == 0 or M == 0:
+        return g[:M]
+    import ctypes as C
+
+    plan = C.c_void_p()
+    _lib.check(L.gi_plan_create(N, M, ld, 1, C.byref(plan)), "gi_plan_create")
+    try:
+        _lib.check(L.gi_gemv_adj(plan, _lib.ptr(Gpad), _lib.ptr(r), _lib.ptr(g), _lib.stream_ptr()),
+                   "gi_gemv_adj")
+        _lib.sync()
+    finally:
+        L.gi_plan_destroy(plan)
+    return g[:M]

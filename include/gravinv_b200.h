@@ -19,6 +19,7 @@
  *   gi_gemm_* / gi_*_batched / gi_hmcb_*
  *                            <- the same lines for a batch of chains (the reference runs one process
  *                               per chain: example/uniformgrid/run_main.sh:18)
+ *   gi_cg_*                  <- inversion/reginv.py:357-491 ConjugateGradient.CG, :631-748 BootStrap
  *   gi_dwt_db4_* / gi_csr_spmv
  *                            <- gravmag/compressor1D.py:45-60, compressor3D.py:47-68 modelcompressor
  *
@@ -350,6 +351,43 @@ int gi_csr_fill(const double *dense_dev, int64_t nrows, int64_t ncols, int64_t r
 /* y = A x for a CSR matrix (int64 indptr[nrows+1], int32 indices, f64 data) */
 int gi_csr_spmv(const int64_t *indptr_dev, const int32_t *indices_dev, const double *data_dev,
                 int64_t nrows, const double *x_dev, double *y_dev, void *stream);
+
+/* ---- regularised conjugate gradient + bootstrap (inversion/reginv.py) ----- */
+/* One handle runs ncols independent CG problems in lockstep over one weighted kernel Aw:
+ *   GI_CG_REGINV    <- ConjugateGradient.CG, reginv.py:357-491 (data/model terms :248-355)
+ *   GI_CG_BOOTSTRAP <- BootStrap.CG, reginv.py:631-713 (MS with beta^2, no prior, :588-629); the row
+ *                      resampling of BootStrap.BSCG (:733-739) enters as per-replicate row
+ *                      multiplicities rowweight[c][l] = how often row l was drawn, so Aw is neither
+ *                      gathered nor copied and all replicates share every pass over it.
+ * ncols == 1 uses the GEMV passes, ncols 2..64 the FP64 tensor-core contractions (ld % 32 == 0).
+ * Three passes over Aw per iteration; scalars (alpha, mu, kstep, norms) never leave the device. */
+#define GI_CG_REGINV 0
+#define GI_CG_BOOTSTRAP 1
+typedef struct gi_cg gi_cg;
+typedef struct {
+    int64_t N, M, ld;
+    int32_t ncols;    /* columns (bootstrap replicates) solved together, 1..64 */
+    int32_t variant;  /* GI_CG_* */
+    gi_reg_params reg; /* reg_kind, nz/ny/nx, beta; alpha/constraint/log_factor are ignored */
+    double q;          /* decay of the regularisation factor (reginv.py:400, 640) */
+    double stop_tol;   /* REGINV: stop when data/N < tol (0.001, :486); BOOTSTRAP: data < tol (0.1, :694) */
+    double rhomin, rhomax; /* bounds on the un-weighted model (reginv.py:434-437) */
+} gi_cg_config;
+/* G_dev (N x ld weighted kernel), wm/wminv/wmsq_dev (ld-vectors, device) stay owned by the caller.
+ * dobs_host [N]; mwapr_host [M] = Wm @ apriorModel or NULL (zero); rowweight_host [ncols][N] or NULL. */
+int gi_cg_create(const gi_cg_config *cfg, const double *G_dev, const double *dobs_host,
+                 const double *wm_dev, const double *wminv_dev, const double *wmsq_dev,
+                 const double *mwapr_host, const double *rowweight_host, void *stream, gi_cg **out);
+int gi_cg_destroy(gi_cg *h);
+/* Run up to maxk iterations from mw0_host [M] = Wm @ initialModel (every column starts there).
+ * Outputs (each optional): iters[ncols] = iterations executed (= entries of regul); regul
+ * [ncols][maxk]; data_misfit / model_misfit [ncols][maxk] in the reference's list order (REGINV:
+ * entry 0 is the start point, `iters` entries; BOOTSTRAP: entry i belongs to iteration i+1). */
+int gi_cg_run(gi_cg *h, const double *mw0_host, int32_t maxk, int32_t *iters_host, double *regul_host,
+              double *data_misfit_host, double *model_misfit_host);
+/* model_inv = WmInv mw [ncols][M]; data_inv = A model_inv [ncols][N] (reginv.py:489-490); mw [ncols][M] */
+int gi_cg_get_result(gi_cg *h, double *model_host, double *data_host, double *mw_host);
+int64_t gi_cg_launch_count(const gi_cg *h);
 
 #ifdef __cplusplus
 }

@@ -772,3 +772,173 @@ def modelcompressor_3d(m, Awcp, mshape):
     CZ, CY, CX = mshape
     c = coeffs_to_array_3d(wavedecn_3d(np.asarray(m).reshape((CZ, CY, CX))))
     return np.squeeze(Awcp @ c.reshape((-1, 1)))
+
+
+# --------------------------------------------------------------------------------------
+# regularised conjugate gradient + bootstrap   inversion/reginv.py  
+# --------------------------------------------------------------------------------------
+class OracleCG:
+    """``ConjugateGradient`` of inversion/reginv.py:22-491 from an explicit weighted kernel.
+    ``A`` is the unweighted kernel (reginv.py:489 forwards the result through it)."""
+
+    def __init__(self, A, dobs, mshape):
+        # reginv.py:120-149 newkernel (the fixed np.sqrt instead of weightfactor)
+        self.A = np.asarray(A, dtype=np.float64)
+        self.Aw, self.wm, self.wminv, self.wmsq = sensitivity_weighting(self.A, 0.5)
+        self.wm = np.sqrt(self.wm * self.wm)  # reginv.py:129 (sqrt of the sum of squares)
+        self.dobs = np.asarray(dobs, dtype=np.float64)
+        self.mshape = tuple(mshape)
+        self.dsize, self.msize = self.A.shape
+        self._R = None
+
+    def R3d(self):
+        if self._R is None:
+            self._R = fd3d(self.mshape)  # reginv.py:151-246 is the same builder as potential.py
+        return self._R
+
+    def data(self, mw):  # reginv.py:248-257
+        return np.linalg.norm(np.dot(self.Aw, mw) - self.dobs) ** 2
+
+    def data_gfun(self, mw):  # reginv.py:259-269
+        return 2 * np.dot(self.Aw.T, (np.dot(self.Aw, mw) - self.dobs))
+
+    def model(self, reg, mw, mwapr, beta):
+        if reg == "MS":  # reginv.py:271-281
+            sq = (mw - mwapr) ** 2
+            return np.sum((self.wmsq * sq) / (sq + beta))
+        if reg == "Damping":  # reginv.py:295-302
+            return np.dot((mw - mwapr).T, (mw - mwapr))
+        if reg == "Smoothness":  # reginv.py:313-321
+            t = self.R3d() @ (mw - mwapr)
+            return np.dot(t.T, t)
+        if reg == "TV":  # reginv.py:333-343
+            t = self.R3d() @ (mw - mwapr)
+            return np.sum(np.sqrt(t ** 2 + beta))
+        raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
+
+    def model_gfun(self, reg, mw, mwapr, beta):
+        if reg == "MS":  # reginv.py:283-293 -- the denominator uses mw*mw, NOT (mw - mwapr)^2
+            return ((2 * beta * self.wmsq) * (mw - mwapr)) / (mw * mw + beta) ** 2
+        if reg == "Damping":  # reginv.py:304-311
+            return 2 * (mw - mwapr)
+        if reg == "Smoothness":  # reginv.py:323-331
+            R = self.R3d()
+            return 2 * R.T @ R @ (mw - mwapr)
+        if reg == "TV":  # reginv.py:345-355
+            R = self.R3d()
+            t1 = R @ (mw - mwapr)
+            return R.T @ (t1 / np.sqrt(t1 ** 2 + beta))
+        raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
+
+    def CG(self, initialModel, apriorModel, boundary, regularization="MS", beta=0.01, q=0.9,
+           maxk=100):
+        """reginv.py:357-491 -> model_inv, data_inv, data_misfit, model_misfit, regul_factor"""
+        reg = regularization
+        mw = self.wm * initialModel
+        mwapr = self.wm * apriorModel
+        rhomin, rhomax = boundary[0], boundary[1]
+        data_misfit, model_misfit, regul_factor = [], [], []
+        for k in range(0, maxk):
+            if k == 0:
+                alpha = 0
+            elif k == 1:
+                alpha = self.data(mw_new) / self.model(reg, mw_new, mwapr, beta)
+            elif self.data(mw) - self.data(mw_new) < 0.01 * self.data(mw):
+                alpha = q * alpha
+            regul_factor.append(alpha)
+            if k == 0:
+                data_misfit.append(self.data(mw) / self.dsize)
+                I = self.data_gfun(mw) + alpha * self.model_gfun(reg, mw, mwapr, beta)
+                model_misfit.append(self.model(reg, mw, mwapr, beta) / self.msize)
+                Iw = I
+            else:
+                I_old, Iw_old, mw = I, Iw, mw_new
+                I = self.data_gfun(mw) + alpha * self.model_gfun(reg, mw, mwapr, beta)
+                mu = np.linalg.norm(I) ** 2 / np.linalg.norm(I_old) ** 2
+                Iw = I + mu * Iw_old
+            kstep = np.dot(Iw.T, I) / (np.linalg.norm(self.Aw @ Iw) ** 2
+                                       + alpha * np.linalg.norm(Iw) ** 2)
+            mw_new = mw - kstep * Iw
+            mtemp = self.wminv * mw_new
+            mtemp[mtemp < rhomin] = rhomin
+            mtemp[mtemp > rhomax] = rhomax
+            mw_new = self.wm * mtemp
+            if k > 0:
+                data_misfit.append(self.data(mw_new) / self.dsize)
+                model_misfit.append(self.model(reg, mw_new, mwapr, beta) / self.msize)
+                if self.data(mw_new) / self.dsize < 0.001:
+                    break
+        model_inv = self.wminv * mw_new
+        return model_inv, self.A @ model_inv, data_misfit, model_misfit, regul_factor
+
+
+class OracleBootStrap(OracleCG):
+    """``BootStrap`` of inversion/reginv.py:494-748 (MS regulariser only, no prior model)."""
+
+    def __init__(self, A, dobs, mshape, boundary, samples=100, beta=0.01, maxk=100):
+        super().__init__(A, dobs, mshape)
+        self.boundary, self.samples, self.beta, self.maxk = boundary, samples, beta, maxk
+
+    def model_MS(self, mw):  # reginv.py:599-606
+        sq = mw * mw
+        return np.sum((self.wmsq * sq) / (sq + self.beta ** 2))
+
+    def model_gfun_MS(self, mw):  # reginv.py:620-629
+        r2 = mw * mw + self.beta ** 2
+        return ((2 * self.wmsq) * (mw * self.beta ** 2)) / (r2 * r2)
+
+    @staticmethod
+    def _data(mw, Aw, dobs):  # reginv.py:588-597
+        return np.linalg.norm(np.dot(Aw, mw) - dobs) ** 2
+
+    def CG(self, Aw, dobs, initialModel):
+        """reginv.py:631-713 -> model_inv, data_misfit, model_misfit, regul_factor"""
+        mw = self.wm * initialModel
+        rhomin, rhomax = self.boundary[0], self.boundary[1]
+        q = 0.9
+        data_misfit, model_misfit, regul_factor = [], [], []
+        for k in range(0, self.maxk):
+            if k == 0:
+                alpha = 0
+            elif k == 1:
+                alpha = self._data(mw_new, Aw, dobs) / self.model_MS(mw_new)
+            elif self._data(mw, Aw, dobs) - self._data(mw_new, Aw, dobs) < 0.01 * self._data(mw, Aw, dobs):
+                alpha = q * alpha
+            regul_factor.append(alpha)
+            if k == 0:
+                I = 2 * np.dot(Aw.T, np.dot(Aw, mw) - dobs) + alpha * self.model_gfun_MS(mw)
+                Iw = I
+            else:
+                I_old, Iw_old, mw = I, Iw, mw_new
+                I = 2 * np.dot(Aw.T, np.dot(Aw, mw) - dobs) + alpha * self.model_gfun_MS(mw)
+                mu = np.linalg.norm(I) ** 2 / np.linalg.norm(I_old) ** 2
+                Iw = I + mu * Iw_old
+            kstep = np.dot(Iw.T, I) / (np.linalg.norm(Aw @ Iw) ** 2 + alpha * np.linalg.norm(Iw) ** 2)
+            mw_new = mw - kstep * Iw
+            mtemp = self.wminv * mw_new
+            mtemp[mtemp < rhomin] = rhomin
+            mtemp[mtemp > rhomax] = rhomax
+            mw_new = self.wm * mtemp
+            if k > 0:
+                if self._data(mw_new, Aw, dobs) < 0.1:
+                    break
+                data_misfit.append(self._data(mw_new, Aw, dobs) / self.dsize)
+                model_misfit.append(self.model_MS(mw_new) / self.msize)
+        return self.wminv * mw_new, data_misfit, model_misfit, regul_factor
+
+    def BSCG(self, initialModel):
+        """reginv.py:715-748: replicate s resamples the observation rows with the legacy global RNG
+        seeded by s (``np.random.seed(s); np.random.choice``) and runs CG on the gathered rows."""
+        model_inv_all = np.zeros((self.samples, self.msize))
+        data_misfit_all = np.zeros((self.samples, self.maxk - 1))
+        model_misfit_all = np.zeros((self.samples, self.maxk - 1))
+        regul_factor_all = np.zeros((self.samples, self.maxk))
+        for sample in range(self.samples):
+            rs = np.random.RandomState(sample)
+            idx = rs.choice(np.arange(0, self.dsize), size=self.dsize, replace=True, p=None)
+            m, dm, mm, rf = self.CG(self.Aw[idx, :], self.dobs[idx], initialModel)
+            model_inv_all[sample, :] = m
+            data_misfit_all[sample, :] = dm  # ValueError when a replicate stopped early, as reginv.py:745
+            model_misfit_all[sample, :] = mm
+            regul_factor_all[sample, :] = rf
+        return model_inv_all, data_misfit_all, model_misfit_all, regul_factor_all
