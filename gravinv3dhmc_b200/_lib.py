@@ -129,6 +129,16 @@ SIGNATURES = {
     "gi_csr_fill": (C.c_int, [_P, _I64, _I64, _I64, _D, _P, _P, _P, _P]),
     "gi_hmc_set_wavelet": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _I64]),
     "gi_csr_spmv": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
+    "gi_stats_create": (C.c_int, [_I64, _I64, C.c_int32, C.POINTER(_P)]),
+    "gi_stats_destroy": (C.c_int, [_P]),
+    "gi_stats_reset": (C.c_int, [_P]),
+    "gi_stats_window": (C.c_int, [_P, _I64, _I64]),
+    "gi_stats_add": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    "gi_stats_result": (C.c_int, [_P, C.c_int32, _P, _P, C.POINTER(_I64), C.POINTER(_I64), _P]),
+    "gi_stats_result_dev": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.POINTER(_I64), C.POINTER(_I64), _P]),
+    "gi_stats_launch_count": (_I64, [_P]),
+    "gi_hmc_attach_stats": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "gi_hmcb_attach_stats": (C.c_int, [_P, _P, _P]),
     "gi_cg_create": (C.c_int, [C.POINTER(CgConfig), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "gi_cg_destroy": (C.c_int, [_P]),
     "gi_cg_run": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),

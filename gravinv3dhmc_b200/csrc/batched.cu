@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "plan.cuh"
+#include "sink.cuh"
 
 namespace gi {
 
@@ -912,6 +913,9 @@ struct gi_hmcb {
     void *hook_user;
     double *g_ext, *red;  // caller-owned piece-major gradient buffer and [2*C] scalar buffer
     int npieces;
+    // on-device sample sink (gi_hmcb_attach_stats): chain c -> slot c
+    gi_stats *stats;
+    const double *stats_scale;
 };
 
 static void hmcb_free(gi_hmcb *h) {
@@ -1241,10 +1245,25 @@ static int hb_run(gi_hmcb *h, int32_t Lmax, double dt, const int32_t *L_dev, gi_
                                                h->mw_cur, h->g_cur, h->d_cur);
     GI_LAUNCH_CHECK();
     h->launches += 2;
+    if (h->stats) {  // accepted models go to the sink without leaving the device
+        StatsMap map;
+        memset(&map, 0, sizeof(map));
+        for (int c = 0; c < nc; ++c) map.fin[c] = 1;  // chains that sat out have accept == 0
+        rc = stats_add_chains(h->stats, map, h->st, h->mw_cur, ld, nc, 0, h->stats_scale, s);
+        if (rc) return rc;
+        h->launches += 2;
+    }
     GI_CUDA(cudaMemcpyAsync(h->st_host, h->st, sizeof(DevState) * C, cudaMemcpyDeviceToHost, s));
     GI_CUDA(cudaStreamSynchronize(s));
     if (results)
         for (int c = 0; c < nc; ++c) results[c] = h->st_host[c].res;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_attach_stats(gi_hmcb *h, gi_stats *stats, const double *scale_dev) {
+    GI_REQUIRE(h, "gi_hmcb_attach_stats: null handle");
+    h->stats = stats;
+    h->stats_scale = scale_dev;
     return GI_OK;
 }
 
@@ -1489,6 +1508,14 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
                                                       h->d, h->x_cur, h->mw_cur, h->g_cur, h->d_cur);
             GI_LAUNCH_CHECK();
             h->launches += 1;
+            if (h->stats) {
+                StatsMap map;
+                memcpy(map.fin, sc.fin, sizeof(map.fin));
+                rc = stats_add_chains(h->stats, map, h->st, h->mw_cur, ld, h->nchains, 0,
+                                      h->stats_scale, s);
+                if (rc) return rc;
+                h->launches += 2;
+            }
             if (x_host) {
                 // the copies run on their own stream, under the next steps' contractions
                 GI_CUDA(cudaEventRecord(h->ev_commit, s));

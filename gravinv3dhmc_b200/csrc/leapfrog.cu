@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "plan.cuh"
+#include "sink.cuh"
 
 namespace gi {
 
@@ -443,6 +444,10 @@ struct gi_hmc {
     const double *wv_data;
     int64_t wv_ncoef;
     double *wv_coef;
+    // on-device sample sink (gi_hmc_attach_stats)
+    gi_stats *stats;
+    int32_t stats_slot;
+    const double *stats_scale;
 };
 
 static void hmc_free(gi_hmc *h) {
@@ -696,9 +701,26 @@ static int run_trajectory(gi_hmc *h, int32_t L, double dt, gi_hmc_result *result
                                                             h->d_cur);
     GI_LAUNCH_CHECK();
     h->launches += 2;
+    if (h->stats) {  // the accepted model goes to the sink without leaving the device
+        StatsMap map;
+        memset(&map, 0, sizeof(map));
+        map.fin[0] = 1;
+        rc = stats_add_chains(h->stats, map, h->st, h->mw_cur, h->cfg.ld, 1, h->stats_slot,
+                              h->stats_scale, s);
+        if (rc) return rc;
+        h->launches += 2;
+    }
     GI_CUDA(cudaMemcpyAsync(h->st_host, h->st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
     GI_CUDA(cudaStreamSynchronize(s));
     if (result) *result = h->st_host->res;
+    return GI_OK;
+}
+
+extern "C" int gi_hmc_attach_stats(gi_hmc *h, gi_stats *stats, int32_t slot, const double *scale_dev) {
+    GI_REQUIRE(h, "gi_hmc_attach_stats: null handle");
+    h->stats = stats;
+    h->stats_slot = slot;
+    h->stats_scale = scale_dev;
     return GI_OK;
 }
 

@@ -237,6 +237,8 @@ class HMCBatch:
         self._h = None
         self._sh = None
         self._ahead = None
+        self.output = "text"   # "text" (the reference's files) | "binary" | "none"  (inversion/sink.py)
+        self.sink = None       # SampleSink(model, nslots=nchains): chain c -> slot c
         _lib.require_cuda()
         mw = self.initial_model
         if constraint == "logarithmic":     # hmc.py:271-273
@@ -464,15 +466,14 @@ class HMCBatch:
         world, rank = getattr(self.model, "world", 1), getattr(self.model, "rank", 0)
         folders = [self.save_folder + str(c) for c in range(nc)]
         write = write and rank == 0  # every rank holds the same chains
-        if write:
-            for fo in folders:
-                if not os.path.exists(fo):
-                    os.mkdir(fo)
-                if os.path.exists(fo + "/model.dat"):
-                    os.remove(fo + "/model.dat")
+        writers = self._writers(write)
+        write = writers[0].mode != "none"
+        self._attach_sink(ndraws, nsamples)
         data_size, model_size = self.dobs.shape[0], self.initial_model.shape[0]
         alpha, target = self.RegulFactor, ndraws + nsamples
         recs, xh = self._stream_buffers()
+        # output "none": the accepted positions stay on the device (the sink, if any, has them)
+        keep_x = write or on_record is not None or self.sink is None
         cap = len(recs)
         nrec, ndone = C.c_int32(), C.c_int32()
         count, fed, inflight = [0] * nc, [0] * nc, [0] * nc
@@ -500,7 +501,7 @@ class HMCBatch:
                 if run.value == 0:
                     break
                 _lib.check(lib.gi_hmcb_stream_advance(self._h, run.value, recs, cap, C.byref(nrec),
-                                                      C.byref(ndone), _lib.ptr(xh)),
+                                                      C.byref(ndone), _lib.ptr(xh) if keep_x else None),
                            "gi_hmcb_stream_advance")
                 self.stream_steps += ndone.value
                 for i in range(nrec.value):
@@ -514,19 +515,17 @@ class HMCBatch:
                     Udn, Umn = r.U_data / data_size, r.U_model / model_size
                     Un = Udn + alpha * Umn
                     if acc:
-                        self.x[c] = xh[i].numpy()
+                        if keep_x:
+                            self.x[c] = xh[i].numpy()
                         if count[c] >= ndraws and write:
-                            with open(folders[c] + "/misfit.dat", "a") as f:
-                                np.savetxt(f, np.array([[r.U, r.U_data, r.U_model, Un, Udn, Umn, alpha]]),
-                                           fmt="%.8f", delimiter=" ")
                             x = self.x[c]
                             if self.constraint == "logarithmic":
                                 mw = (self.low + self.high * np.e ** (self.log_factor * x)) / \
                                      (1 + np.e ** (self.log_factor * x))
                             else:
                                 mw = x
-                            with open(folders[c] + "/model.dat", "a") as f:
-                                np.savetxt(f, (self.wminv * mw)[None, :], fmt="%.8f", delimiter=" ")
+                            writers[c].append([r.U, r.U_data, r.U_model, Un, Udn, Umn, alpha],
+                                              self.wminv * mw)
                         count[c] += 1
                         if count[c] >= target:
                             live[c] = False
@@ -544,18 +543,37 @@ class HMCBatch:
                         ahead.disable(c)
         finally:
             ahead.stop()
+        if not keep_x:  # the device's current positions, once (a chain may have run a queued
+            # proposal past its target; the recorded statistics are gated and unaffected)
+            _lib.check(lib.gi_hmcb_get_state(self._h, _lib.ptr(self.x), None, None), "gi_hmcb_get_state")
         return self.x
+
+    def _writers(self, write=True):
+        from .sink import SampleWriter
+
+        mode = self.output if write else "none"
+        return [SampleWriter(self.save_folder + str(c), mode, self.model.M) for c in range(self.nchains)]
+
+    def _attach_sink(self, ndraws, nsamples):
+        if self.sink is None:
+            return
+        if self._h is None:
+            raise NotImplementedError("the device sink needs the device driver")
+        if self.sink.nslots < self.nchains:
+            raise ValueError("SampleSink needs one slot per chain")
+        _lib.check(_lib.lib().gi_hmcb_attach_stats(self._h, self.sink.h, _lib.ptr(self.model.wminv_dev)),
+                   "gi_hmcb_attach_stats")
+        if not self.sink.user_window:
+            self.sink.window(ndraws, nsamples)
 
     def sample(self, nsamples, ndraws, max_proposals=None):
         """hmc.py:252-343 for every chain of the batch."""
         nc = self.nchains
         folders = [self.save_folder + str(c) for c in range(nc)]
         writes = getattr(self.model, "rank", 0) == 0
-        for fo in folders if writes else []:
-            if not os.path.exists(fo):
-                os.mkdir(fo)
-            if os.path.exists(fo + "/model.dat"):
-                os.remove(fo + "/model.dat")
+        writers = self._writers(writes)
+        writes = writers[0].mode != "none"
+        self._attach_sink(ndraws, nsamples)
         data_size, model_size = self.dobs.shape[0], self.initial_model.shape[0]
         alpha = self.RegulFactor
         count = [0] * nc      # accepted proposals (the reference's i)
@@ -574,17 +592,13 @@ class HMCBatch:
                 Un = Udn + alpha * Umn
                 if acc:
                     if count[c] >= ndraws and writes:
-                        with open(folders[c] + "/misfit.dat", "a") as f:
-                            np.savetxt(f, np.array([[U, Ud, Um, Un, Udn, Umn, alpha]]), fmt="%.8f",
-                                       delimiter=" ")
                         x = self.x[c]
                         if self.constraint == "logarithmic":
                             mw = (self.low + self.high * np.e ** (self.log_factor * x)) / \
                                  (1 + np.e ** (self.log_factor * x))
                         else:
                             mw = x
-                        with open(folders[c] + "/model.dat", "a") as f:
-                            np.savetxt(f, (self.wminv * mw)[None, :], fmt="%.8f", delimiter=" ")
+                        writers[c].append([U, Ud, Um, Un, Udn, Umn, alpha], self.wminv * mw)
                     count[c] += 1
                 if not self.quiet:
                     print("chain {}: {:.2%}, misfit(total, data, alpha, model)=({:.7f},{:.7f},{:.2f},"

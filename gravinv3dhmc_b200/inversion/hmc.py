@@ -47,6 +47,8 @@ class HamitonianMC:
         self._h = None          # gi_hmc handle (single GPU)
         self._synced = None     # host array whose contents the device state mirrors
         self.proposals = []     # (L, accept) log of this chain
+        self.output = "text"    # "text" (the reference's files) | "binary" | "none"  (inversion/sink.py)
+        self.sink = None        # SampleSink: on-device posterior mean / std of the accepted models
         self._philox_counter = 0
 
     # ---- reference helper API ---------------------------------------------------------------
@@ -100,6 +102,9 @@ class HamitonianMC:
                    "gi_hmc_create")
         self._h = h
         self._alpha = alpha
+        if self.sink is not None:
+            _lib.check(L.gi_hmc_attach_stats(h, self.sink.h, int(getattr(self, "sink_slot", 0)),
+                                             _lib.ptr(m.wminv_dev)), "gi_hmc_attach_stats")
         if m.wavelet in ("1D", "3D"):  # potential.py:693-696: forward through the compressed kernel
             nz, ny, nx = (int(v) for v in m.mshape)
             cp = m.Awcp
@@ -189,12 +194,19 @@ class HamitonianMC:
     # ---- the chain ------------------------------------------------------------------------------
     def sample(self, nsamples, ndraws, **kwargs):
         """hmc.py:252-343"""
+        from .sink import SampleWriter
+
         writes = (not self._sharded()) or self.model.rank == 0
-        if writes:
-            if not os.path.exists(self.save_folder):
-                os.mkdir(self.save_folder)
-            if os.path.exists(self.save_folder + "/" + "model" + ".dat"):
-                os.remove(self.save_folder + "/" + "model" + ".dat")
+        writer = SampleWriter(self.save_folder, self.output if writes else "none", self.model.M)
+        if self.sink is not None:
+            if self._sharded():
+                raise NotImplementedError("the device sink needs the single-GPU handle")
+            if self._h is not None:  # created before the sink was set
+                _lib.check(_lib.lib().gi_hmc_attach_stats(
+                    self._h, self.sink.h, int(getattr(self, "sink_slot", 0)),
+                    _lib.ptr(self.model.wminv_dev)), "gi_hmc_attach_stats")
+            if not self.sink.user_window:  # the recorded samples: hmc.py:318
+                self.sink.window(ndraws, nsamples)
         np.random.seed(self.seed)
         _, WmInv, _ = self._kernelw()
         wminv = WmInv.diagonal()
@@ -224,16 +236,15 @@ class HamitonianMC:
             U_model_normed = U_model / model_size
             U_normed = U_data_normed + alpha * U_model_normed
             if AcceptFlag:
-                if i >= ndraws and writes:
+                if i >= ndraws and writer.mode != "none":
                     misfit[0, :] = [U, U_data, U_model, U_normed, U_data_normed, U_model_normed, alpha]
-                    self._save_misfit_add(misfit)
                     if self.constraint == "logarithmic":
                         mw = (self.low + self.high * np.e ** (self.log_factor * x)) / \
                              (1 + np.e ** (self.log_factor * x))
                     else:
                         mw = x
                     m_cache[0, :] = wminv * mw      # m = WmInv @ mw
-                    self._save_models_add(m_cache)
+                    writer.append(misfit, m_cache)
                 i += 1
             ncount += 1
             if i > -1:

@@ -20,6 +20,8 @@
  *                            <- the same lines for a batch of chains (the reference runs one process
  *                               per chain: example/uniformgrid/run_main.sh:18)
  *   gi_cg_*                  <- inversion/reginv.py:357-491 ConjugateGradient.CG, :631-748 BootStrap
+ *   gi_stats_*               <- inversion/hmc.py:241-249 (model.dat sink) + example/uniformgrid/
+ *                               plot_uniform.py:103-114 (posterior mean / std and their forward data)
  *   gi_dwt_db4_* / gi_csr_spmv
  *                            <- gravmag/compressor1D.py:45-60, compressor3D.py:47-68 modelcompressor
  *
@@ -388,6 +390,36 @@ int gi_cg_run(gi_cg *h, const double *mw0_host, int32_t maxk, int32_t *iters_hos
 /* model_inv = WmInv mw [ncols][M]; data_inv = A model_inv [ncols][N] (reginv.py:489-490); mw [ncols][M] */
 int gi_cg_get_result(gi_cg *h, double *model_host, double *data_host, double *mw_host);
 int64_t gi_cg_launch_count(const gi_cg *h);
+
+/* ---- on-device sample sink ------------------------------------------------ */
+/* Replaces the text sink of inversion/hmc.py:241-249 (model.dat: one "%.8f" row of M numbers per
+ * accepted sample) and the post-processing of example/uniformgrid/plot_uniform.py:44-135 (np.mean /
+ * np.std over the last `last` rows, forward data of both): every sampler handle that has a sink
+ * attached adds m = scale .* mw of each ACCEPTED proposal to a Welford accumulator right after the
+ * commit, gated on the device by the Metropolis flag and by the window below -- no device->host
+ * traffic.  nslots accumulators (one per chain, <= 64) plus pooled statistics over all of them. */
+typedef struct gi_stats gi_stats;
+int gi_stats_create(int64_t M, int64_t ld, int32_t nslots, gi_stats **out);
+int gi_stats_destroy(gi_stats *s);
+int gi_stats_reset(gi_stats *s);
+/* per slot: ignore the first `skip` accepted samples, then accumulate `take` (<= 0: no limit);
+ * the reference's ndraws / nsamples (hmc.py:295, 318) or nsamples - last / last of the plot script */
+int gi_stats_window(gi_stats *s, int64_t skip, int64_t take);
+/* offer one accepted sample given as a device vector (ld entries); scale_dev may be NULL */
+int gi_stats_add(gi_stats *s, int32_t slot, const double *mw_dev, const double *scale_dev, void *stream);
+/* mean and population standard deviation (np.std, ddof = 0) of a slot, slot = -1: pooled over all
+ * slots.  count = samples accumulated, seen = accepted samples offered.  The _dev variant writes
+ * device vectors of ld entries, optionally scaled (scale = Wm gives the weighted models whose forward
+ * data Aw (Wm m) are plot_uniform.py:112-114's dpre_mean / dpre_std). */
+int gi_stats_result(gi_stats *s, int32_t slot, double *mean_host, double *std_host, int64_t *count,
+                    int64_t *seen, void *stream);
+int gi_stats_result_dev(gi_stats *s, int32_t slot, const double *scale_dev, double *mean_dev,
+                        double *std_dev, int64_t *count, int64_t *seen, void *stream);
+int64_t gi_stats_launch_count(const gi_stats *s);
+/* attach (or detach with stats = NULL) a sink: gi_hmc adds to `slot`, gi_hmcb chain c to slot c;
+ * scale_dev (device, ld entries, e.g. WmInv; caller-owned) maps mw to the recorded model */
+int gi_hmc_attach_stats(gi_hmc *h, gi_stats *stats, int32_t slot, const double *scale_dev);
+int gi_hmcb_attach_stats(gi_hmcb *h, gi_stats *stats, const double *scale_dev);
 
 #ifdef __cplusplus
 }
