@@ -17,31 +17,13 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "prism_math.cuh"
 
 namespace gi {
 
 // ---------------------------------------------------------------------------------------------
 // prism gz
 // ---------------------------------------------------------------------------------------------
-// _prism.pyx:21 spells pi with more digits than a double holds; this is the same binary64.
-__device__ __constant__ const double kPi = 3.1415926535897931159979634685441851615906;
-
-__device__ __forceinline__ double prism_safe_atan2(double y, double x) {
-    // _prism.pyx:16-26
-    if (y == 0.0) return 0.0;
-    double a = atan2(y, x);
-    if (x < 0.0) {
-        if (y > 0.0) a = __dsub_rn(a, kPi);
-        else if (y < 0.0) a = __dadd_rn(a, kPi);
-    }
-    return a;
-}
-
-__device__ __forceinline__ double prism_safe_log(double x) {
-    // _prism.pyx:28-34
-    return (x == 0.0) ? 0.0 : log(x);
-}
-
 __device__ __forceinline__ double prism_corner(double x, double y, double z) {
     // r = sqrt(x**2 + y**2 + z**2)  (_prism.pyx:286);  kernelz (_prism.pyx:49-50):
     // -(x*log(y + r) + y*log(x + r) - z*atan2(x*y, z*r))

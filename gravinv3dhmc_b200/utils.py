@@ -1,4 +1,5 @@
-"""Model-vector compaction for topography-carved meshes (reference utils.py:714-749)."""
+"""Model-vector compaction for topography-carved meshes (reference utils.py:714-749) and the
+direction helpers of the magnetic fields (utils.py:420-474)."""
 import numpy as np
 
 
@@ -22,3 +23,16 @@ def carve2rho(rhocarve, rho, mask):
     keep = _keep(rho.shape[0], mask)
     rho[keep] = np.asarray(rhocarve)[: int(keep.sum())]
     return rho.copy()
+
+
+def dircos(inc, dec):
+    """unit vector [x, y, z] (x North, y East, z Down) of an inclination / declination in degrees
+    (utils.py:448-474)"""
+    d2r = np.pi / 180.
+    return [np.cos(d2r * inc) * np.cos(d2r * dec), np.cos(d2r * inc) * np.sin(d2r * dec),
+            np.sin(d2r * inc)]
+
+
+def ang2vec(intensity, inc, dec):
+    """vector(s) of the given intensity along (inc, dec) (utils.py:420-445)"""
+    return np.transpose([intensity * i for i in dircos(inc, dec)])

@@ -111,6 +111,32 @@ int gi_tess_gz_leafcount(const double *lon_dev, const double *sinlat_dev, const 
                          double ratio, double *leaves_dev, int64_t ld, int32_t *status_dev,
                          void *stream);
 
+/* ---- the other prism fields (gravmag/_prism.pyx) --------------------------- */
+/* G[l*ld + c] = scale * sum over the 8 corners of prism c at observation l of the corner kernel of
+ * `field` (_prism.pyx:36-70), same layout / row sharding as gi_prism_gz_assemble.  Replaces the
+ * per-prism Cython calls potential :484, gx :206, gy :235, gz :265, gxx :294, gxy :324, gxz :358,
+ * gyy :392, gyz :421, gzz :455 (the three mixed components with the displaced radius of
+ * :345-350 / :380-385 / :442-447), tf :72 (vec3 = the unit vector f of the regional field: the
+ * kernel is f.(V f)) and the rows of V applied to vec3 (bx :116, by :146, bz :176). */
+#define GI_FIELD_POTENTIAL 0
+#define GI_FIELD_GX 1
+#define GI_FIELD_GY 2
+#define GI_FIELD_GZ 3
+#define GI_FIELD_GXX 4
+#define GI_FIELD_GXY 5
+#define GI_FIELD_GXZ 6
+#define GI_FIELD_GYY 7
+#define GI_FIELD_GYZ 8
+#define GI_FIELD_GZZ 9
+#define GI_FIELD_TF 10
+#define GI_FIELD_VX 11
+#define GI_FIELD_VY 12
+#define GI_FIELD_VZ 13
+int gi_prism_field_assemble(int32_t field, const double *xp_dev, const double *yp_dev,
+                            const double *zp_dev, int64_t nrows, const double *bounds_dev, int64_t M,
+                            double scale, const double *vec3_host, double *G_dev, int64_t ld,
+                            void *stream);
+
 /* ---- sensitivity weighting (potential.py:232-264) ---------------------------------------- */
 /* out[c] (+)= sum_l G[l][c]^2, rows summed sequentially in row order. */
 int gi_colsumsq(const double *G_dev, int64_t nrows, int64_t M, int64_t ld, double *out_dev,

@@ -47,7 +47,7 @@ RATIO_G = 1.6  # gravmag/tesseroid.py:77
 # --------------------------------------------------------------------------------------
 def build(force: bool = False) -> str:
     so = os.path.join(HERE, "_build", "liboracle.so")
-    srcs = [os.path.join(HERE, "csrc", f) for f in ("oracle_prism.c", "oracle_tess.c")]
+    srcs = [os.path.join(HERE, "csrc", f) for f in ("oracle_prism.c", "oracle_tess.c", "oracle_fields.c")]
     stale = (not os.path.exists(so)) or any(
         os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
@@ -72,6 +72,9 @@ def _lib():
         L.oracle_tess_leaves.argtypes = [dp, dp, dp, dp, i64, dp, i64, ctypes.c_double,
                                          ctypes.c_void_p, i64]
         L.oracle_tess_leaves.restype = ctypes.c_int
+        L.oracle_prism_field.argtypes = [ctypes.c_int, dp, dp, dp, i64, dp, i64, ctypes.c_double, dp,
+                                         dp, i64, dp, ctypes.c_int, dp]
+        L.oracle_prism_field.restype = ctypes.c_int
         _LIB = L
     return _LIB
 
@@ -106,6 +109,67 @@ def prism_gz(xp, yp, zp, bounds, dens=None, threads: int = 1):
         L.oracle_prism_gz(_dp(xp[lo:hi]), _dp(yp[lo:hi]), _dp(zp[lo:hi]), hi - lo, _dp(bounds), M,
                           scale, _dp(K[lo:hi]), M, None if d is None else _dp(d),
                           None if d is None else _dp(res[lo:hi]))
+
+    _run_rows(run, N, threads)
+    return res, K
+
+
+# constants.py:26,37,41,50
+SI2EOTVOS = 1000000000.0
+CM = 10. ** (-7)
+T2NT = 10. ** (6)
+G0 = 9.80
+PRISM_FIELDS = {"potential": 0, "geoid": 0, "gx": 1, "gy": 2, "gz": 3, "gxx": 4, "gxy": 5, "gxz": 6,
+                "gyy": 7, "gyz": 8, "gzz": 9, "tf": 10, "bx": 11, "by": 12, "bz": 13}
+
+
+def prism_field_scale(field):
+    """the factor gravmag/prism.py applies after the corner sums (:150, 178, 231, 367, 729, 777)"""
+    if field == "potential":
+        return G
+    if field == "geoid":
+        return G / G0
+    if field in ("gx", "gy", "gz"):
+        return G * SI2MGAL
+    if field in ("tf", "bx", "by", "bz"):
+        return CM * T2NT
+    return G * SI2EOTVOS
+
+
+def dircos(inc, dec):
+    """utils.py:448-474"""
+    d2r = np.pi / 180.
+    return [np.cos(d2r * inc) * np.cos(d2r * dec), np.cos(d2r * inc) * np.sin(d2r * dec),
+            np.sin(d2r * inc)]
+
+
+def prism_field(field, xp, yp, zp, bounds, dens=None, inc=None, dec=None, mag=None, threads: int = 1):
+    """(result, kernel2d) of gravmag/prism.py's `potential, geoid, gx .. gzz, tf` (:875-982) and the
+    result of `bx, by, bz` (:735-870, kernel2d = None) for an explicit bounds table.  ``dens``: per
+    prism densities; ``mag``: per-prism magnetisation vectors [M,3] (tf, bx, by, bz)."""
+    xp, yp, zp, bounds = _c(xp), _c(yp), _c(zp), _c(bounds).reshape(-1, 6)
+    if xp.shape != yp.shape or xp.shape != zp.shape:
+        raise ValueError("Input arrays xp, yp, and zp must have same length!")
+    N, M = xp.shape[0], bounds.shape[0]
+    code = PRISM_FIELDS[field]
+    want_kernel = code <= 10
+    K = np.zeros((N, M)) if want_kernel else None
+    res = np.zeros(N)
+    vec = _c(dircos(inc, dec)) if field == "tf" else _c([0.0, 0.0, 0.0])
+    if code >= 10:
+        w = None if mag is None else _c(mag).reshape(M, 3)
+        nw = 3
+    else:
+        w = None if dens is None else _c(dens)
+        nw = 1
+    L = _lib()
+
+    def run(lo, hi):
+        if hi <= lo:
+            return
+        L.oracle_prism_field(code, _dp(xp[lo:hi]), _dp(yp[lo:hi]), _dp(zp[lo:hi]), hi - lo, _dp(bounds),
+                             M, prism_field_scale(field), _dp(vec), None if K is None else _dp(K[lo:hi]),
+                             M, None if w is None else _dp(w), nw, None if w is None else _dp(res[lo:hi]))
 
     _run_rows(run, N, threads)
     return res, K
