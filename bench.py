@@ -199,6 +199,10 @@ def cpu_reference_arm(workload, sample_rows, steps, cores=None, warm=0):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def gpu_arm(args):
+    if os.environ.get("GI_BENCH_WATCHDOG"):  # diagnostics: dump all stacks and exit if the run hangs
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["GI_BENCH_WATCHDOG"]), exit=True)
     import torch
     import torch.distributed as dist
 
@@ -435,22 +439,33 @@ def gpu_arm(args):
         # prepared on host threads while the GPU runs.  Measured over the steady-state window that
         # ends when the first chain has completed its quota of proposals (after that the batch
         # drains and chains run dry one by one).
-        nprop = max(2, int(round(args.steps / 12.5)) + 1)
+        nprop = max(4, int(round(args.steps / 12.5)) + 2)
         bt.proposals = [[] for _ in range(nch)]
         window = {}
 
         def on_record(c, r, acc):
-            if not window and len(bt.proposals[c]) >= nprop:
+            # steady state: the window opens when the first proposal of the batch has finished (the
+            # pipeline of draws is filled, every chain is mid-trajectory) and closes when the first
+            # chain has completed its quota (after that the batch drains, chains run dry one by one)
+            if "t0" not in window:
                 torch.cuda.synchronize()
-                window.update(t=time.perf_counter() - t0, steps=bt.stream_steps,
-                              props=sum(len(q) for q in bt.proposals))
+                window.update(t0=time.perf_counter(), s0=bt.stream_steps,
+                              p0=sum(len(q) for q in bt.proposals))
+            if "t" not in window and len(bt.proposals[c]) >= nprop:
+                torch.cuda.synchronize()
+                window.update(t=time.perf_counter() - window["t0"], steps=bt.stream_steps - window["s0"],
+                              props=sum(len(q) for q in bt.proposals) - window["p0"])
 
         bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
-        api = ("HMCBatch.stream -> gi_hmcb_stream_feed/advance (host RNG in the reference's order, "
-               "per-chain L in [5,20], chains restart inside the step they finish in; steady-state "
-               "window of %d batch steps%s)" % (window["steps"], "; row-sharded, NCCL all-reduce hooks"
-                                               if world > 1 else ""))
+        api = ("HMCBatch.stream -> gi_hmcb_stream_feed_dev/advance (host RNG in the reference's order "
+               "on background threads, draws staged host->device on a side stream, per-chain L in "
+               "[5,20], chains restart inside the step they finish in; steady-state window of %d "
+               "batch steps%s)" % (window["steps"], "; row-sharded, draws shared through a /dev/shm "
+                                   "ring, NCCL all-reduce hooks" if world > 1 else ""))
         torch.cuda.synchronize()
+        if os.environ.get("GI_STREAM_PROFILE") and rank == 0:
+            print("stream profile (whole run, s):", bt.stream_profile, "steps", bt.stream_steps,
+                  file=sys.stderr)
         # every chain takes one leapfrog step per batch step inside the window
         steps_done, t_e2e, nprops_done = nch * window["steps"], window["t"], window["props"]
         if world > 1:

@@ -136,70 +136,216 @@ class _ShardedBatchState:
             self.d_cur[idx] = eng.d[idx]
 
 
+class _DrawRing:
+    """Per-chain ring of draw slots shared by the ranks of ONE node.  Slot (c, k % depth) carries
+    proposal k of chain c: `[p0 (M doubles) | L | u]`.  The chain's owner rank generates straight into
+    the slot and publishes `ready[c][slot] = k + 1`; every rank copies the slot to its GPU and
+    publishes `done[rank][c] = k + 1`; the owner rewrites a slot only when every rank is done with
+    its previous occupant.  The backing store is a memory-mapped file under /dev/shm (row-sharded
+    runs; registered with CUDA so the host->device copies read it directly) or pinned memory (one
+    rank).  No collective and no device work of another rank is involved, so the threads that use
+    it can never entangle with the NCCL all-reduces of the device loop."""
+
+    def __init__(self, nchains, M, world=1, rank=0, depth=3, path=None, create=False):
+        import torch
+
+        self.nc, self.M, self.world, self.rank, self.depth = nchains, M, world, rank, depth
+        nctl = nchains * depth + world * nchains
+        ndata = nchains * depth * (M + 2)
+        self.path, self.mm, self.registered = path, None, False
+        if path is None:
+            self.ctl = np.zeros(nctl, dtype=np.int64)
+            self.tdata = torch.zeros(ndata, dtype=torch.float64).pin_memory()
+            data = self.tdata.numpy()
+        else:
+            import mmap
+
+            off = (8 * nctl + 4095) // 4096 * 4096
+            nbytes = off + 8 * ndata
+            if create:
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+            self.f = open(path, "r+b")
+            self.mm = mmap.mmap(self.f.fileno(), nbytes)
+            self.ctl = np.frombuffer(self.mm, dtype=np.int64, count=nctl)
+            data = np.frombuffer(self.mm, dtype=np.float64, count=ndata, offset=off)
+            self.tdata = torch.from_numpy(data)
+            # page-lock the mapping so cudaMemcpyAsync reads it directly (else torch stages the copy)
+            if torch.cuda.is_available():
+                rc = torch.cuda.cudart().cudaHostRegister(self.tdata.data_ptr(), 8 * ndata, 0)
+                self.registered = int(rc) == 0
+        self.ready = self.ctl[: nchains * depth].reshape(nchains, depth)
+        self.done = self.ctl[nchains * depth:].reshape(world, nchains)
+        self.data = data.reshape(nchains, depth, M + 2)
+        self.tdata = self.tdata.view(nchains, depth, M + 2)
+        self.abort = False
+
+    def writable(self, c, k):
+        """may the owner generate proposal k of chain c now?"""
+        return int(self.done[:, c].min()) >= k - self.depth + 1
+
+    def publish(self, c, k):
+        self.ready[c, k % self.depth] = k + 1  # after the payload (x86 stores are not reordered)
+
+    def wait_ready(self, c, k):
+        import time
+
+        pause = 20e-6
+        while int(self.ready[c, k % self.depth]) != k + 1:
+            if self.abort:
+                raise RuntimeError("draw ring closed")
+            time.sleep(pause)
+            pause = min(pause * 1.5, 1e-3)
+
+    def release(self, c, k):
+        self.done[self.rank, c] = k + 1
+
+    def close(self):
+        self.abort = True
+        if self.mm is not None:
+            if self.registered:
+                import torch
+
+                torch.cuda.cudart().cudaHostUnregister(self.tdata.data_ptr())
+            self.ready = self.done = self.ctl = self.data = self.tdata = None
+            try:
+                self.mm.close()
+                self.f.close()
+            except (BufferError, ValueError):
+                pass
+            self.mm = None
+
+
 class _DrawAhead:
     """Prepares the draws of upcoming proposals -- (L, p0 = randn(M)*Sigma, u) per chain, consumed
     from `RandomState(seed + c)` in the reference's order (hmc.py:297,95,165) -- on background
-    threads while the GPU runs (numpy's generators and the ctypes calls both release the GIL).
-    Chain c is served by worker c % nworkers, so every chain's stream is consumed sequentially."""
+    threads while the GPU runs (numpy's generators release the GIL), straight into the chain's
+    `_DrawRing` slots.  Chain c is served by worker (index of c among the owned chains) % nworkers,
+    so every chain's stream is consumed sequentially.  Row-sharded runs: chain c is drawn by its
+    owner rank only (`owned[c]`)."""
 
-    def __init__(self, streams, Lrange, M, Sigma, depth=2, nworkers=None, owned=None):
-        self.streams, self.Lrange, self.M, self.Sigma, self.depth = streams, Lrange, M, Sigma, depth
-        self.ready = [collections.deque() for _ in streams]
-        # row-sharded runs: every rank needs the same draws, so chain c is drawn by rank c % world
-        # only and broadcast (`owned[c]` False = another rank's chain)
-        self.enabled = [True] * len(streams) if owned is None else list(owned)
-        self.cv = threading.Condition()
+    def __init__(self, streams, Lrange, M, Sigma, ring, nworkers=None, owned=None):
+        self.streams, self.Lrange, self.M, self.Sigma, self.ring = streams, Lrange, M, Sigma, ring
+        self.mine = [c for c in range(len(streams)) if owned is None or owned[c]]
+        self.produced = [0] * len(streams)
+        self.limit = None  # proposals per chain (None: no limit)
         self.stop_flag = False
-        n = nworkers or max(1, min(8, (os.cpu_count() or 2) // 2, len(streams)))
+        self.error = None
+        n = nworkers or max(1, min(8, (os.cpu_count() or 2) // 2))
+        n = max(1, min(n, len(self.mine)))
         self.workers = [threading.Thread(target=self._run, args=(k, n), daemon=True) for k in range(n)]
 
     def start(self):
         for w in self.workers:
             w.start()
 
-    def _todo(self, k, n):
-        return [c for c in range(k, len(self.streams), n)
-                if self.enabled[c] and len(self.ready[c]) < self.depth]
-
     def _run(self, k, n):
-        while True:
-            with self.cv:
-                while not self.stop_flag and not self._todo(k, n):
-                    self.cv.wait(0.05)
-                if self.stop_flag:
-                    return
-                todo = self._todo(k, n)
-            for c in todo:
-                rs = self.streams[c]
-                L = int(rs.randint(self.Lrange[0], self.Lrange[1] + 1))
-                p0 = rs.randn(self.M) * self.Sigma
-                u = float(rs.rand())
-                with self.cv:
-                    self.ready[c].append((L, p0, u))
-                    self.cv.notify_all()
+        import time
 
-    def wait_primed(self):
-        with self.cv:
-            while any(self.enabled[c] and len(self.ready[c]) < self.depth
-                      for c in range(len(self.streams))):
-                self.cv.wait(0.05)
+        ring, M = self.ring, self.M
+        chains = self.mine[k::n]
+        try:
+            while not self.stop_flag:
+                busy = False
+                for c in chains:
+                    kk = self.produced[c]
+                    if (self.limit is not None and kk >= self.limit) or not ring.writable(c, kk):
+                        continue
+                    rs = self.streams[c]
+                    row = ring.data[c, kk % ring.depth]
+                    L = int(rs.randint(self.Lrange[0], self.Lrange[1] + 1))
+                    np.multiply(rs.randn(M), self.Sigma, out=row[:M])
+                    row[M], row[M + 1] = L, float(rs.rand())
+                    ring.publish(c, kk)
+                    self.produced[c] = kk + 1
+                    busy = True
+                    if self.stop_flag:
+                        return
+                if not busy:
+                    time.sleep(0.0005)
+        except BaseException as e:  # noqa: BLE001  (a closed ring during shutdown ends the worker)
+            if not self.stop_flag:
+                self.error = e
+
+    def wait_primed(self, depth=2):
+        import time
+
+        while any(self.produced[c] < min(depth, self.limit or depth) for c in self.mine):
+            if self.error is not None:
+                raise RuntimeError("draw worker failed") from self.error
+            time.sleep(0.001)
+
+    def stop(self):
+        self.stop_flag = True
+        for w in self.workers:
+            w.join(timeout=30)
+
+
+class _Stager(threading.Thread):
+    """Moves prepared draws to the device AHEAD of the sampler, off its stream: for every request
+    (a chain index, issued by the sampler's deterministic main loop) it waits for the chain's next
+    slot of the `_DrawRing`, copies it to a device slot on a SIDE stream, synchronises only that
+    stream and releases the ring slot.  The sampler then feeds a proposal with a device-to-device
+    copy on its own stream: the host-side exchange and the host->device transfer overlap the
+    contractions already queued."""
+
+    SLOTS = 4  # per chain: two proposals queued in the handle + two staged
+
+    def __init__(self, ring, nchains, M, dev):
+        super().__init__(daemon=True)
+        import queue
+
+        torch = _lib.require_cuda()
+        self.torch, self.ring, self.nc, self.M, self.dev = torch, ring, nchains, M, dev
+        self.req = queue.Queue()
+        self.ready = [collections.deque() for _ in range(nchains)]
+        self.cv = threading.Condition()
+        self.error = None
+        self.slots = torch.zeros((nchains, self.SLOTS, M + 2), dtype=torch.float64, device=dev)
+        self.bytes_h2d = 0
+
+    def request(self, c):
+        self.req.put(c)
+
+    def run(self):
+        torch, ring, M = self.torch, self.ring, self.M
+        try:
+            torch.cuda.set_device(self.dev)
+            side = torch.cuda.Stream(self.dev)
+            count = [0] * self.nc
+            with torch.cuda.stream(side):
+                while True:
+                    c = self.req.get()
+                    if c is None:
+                        return
+                    k = count[c]
+                    count[c] += 1
+                    buf = self.slots[c, k % self.SLOTS]
+                    ring.wait_ready(c, k)
+                    row = ring.data[c, k % ring.depth]
+                    L, u = int(row[M]), float(row[M + 1])
+                    buf.copy_(ring.tdata[c, k % ring.depth], non_blocking=True)
+                    side.synchronize()  # the side stream only
+                    ring.release(c, k)
+                    self.bytes_h2d += 8 * (M + 2)
+                    with self.cv:
+                        self.ready[c].append((L, u, buf[:M]))
+                        self.cv.notify_all()
+        except BaseException as e:  # noqa: BLE001  (surfaced by take())
+            with self.cv:
+                self.error = e
+                self.cv.notify_all()
 
     def take(self, c):
         with self.cv:
             while not self.ready[c]:
+                if self.error is not None:
+                    raise RuntimeError("draw stager failed") from self.error
                 self.cv.wait(0.05)
-            d = self.ready[c].popleft()
-            self.cv.notify_all()
-        return d
-
-    def disable(self, c):
-        with self.cv:
-            self.enabled[c] = False
+            return self.ready[c].popleft()
 
     def stop(self):
-        with self.cv:
-            self.stop_flag = True
-            self.cv.notify_all()
+        self.req.put(None)
 
 
 class HMCBatch:
@@ -407,40 +553,47 @@ class HMCBatch:
                            "gi_hmcb_get_state")
         return out
 
-    def start_draws(self, wait=False):
+    def start_draws(self, wait=False, limit=None):
         """start preparing the draws of the next proposals on background threads (optional; `stream`
-        does it itself).  `wait=True` returns once two proposals per chain are ready."""
+        does it itself).  `wait=True` returns once two proposals per chain are ready; `limit` caps
+        the proposals drawn per chain."""
         world, rank = getattr(self.model, "world", 1), getattr(self.model, "rank", 0)
-        self._owner = [c % world for c in range(self.nchains)]
-        owned = [o == rank for o in self._owner] if (world > 1 and self._sh is None) else None
-        self._ahead = _DrawAhead(self.streams, self.Lrange, self.model.M, self.Sigma, owned=owned)
+        nc, M = self.nchains, self.model.M
+        sharded = world > 1 and self._sh is None
+        self._owner = [c % world for c in range(nc)]
+        owned = [o == rank for o in self._owner] if sharded else None
+        if sharded:
+            import tempfile
+
+            import torch.distributed as dist
+
+            if int(os.environ.get("LOCAL_WORLD_SIZE", world)) != world:
+                raise NotImplementedError("the streaming sampler shares draws through host memory: "
+                                          "all ranks must run on one node")
+            # rank 0 creates the ring file, the others map it (collective: every rank gets here)
+            name = [None]
+            if rank == 0:
+                fd, name[0] = tempfile.mkstemp(prefix="gi_draws_",
+                                               dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+                os.close(fd)
+                ring = _DrawRing(nc, M, world, rank, path=name[0], create=True)
+            dist.broadcast_object_list(name, src=0, group=self.model.group)
+            if rank != 0:
+                ring = _DrawRing(nc, M, world, rank, path=name[0])
+            dist.barrier(group=self.model.group)
+            if rank == 0:
+                os.unlink(name[0])  # every rank has it mapped; the memory lives until they unmap
+        else:
+            ring = _DrawRing(nc, M)
+        # host threads for the draws: this rank's share of the cores, minus the sampler and stager threads
+        nw = max(1, min(8, (os.cpu_count() or 2) // max(world, 1) - 2))
+        self._ahead = _DrawAhead(self.streams, self.Lrange, M, self.Sigma, ring, nworkers=nw, owned=owned)
+        self._ahead.limit = limit
         self._ahead.start()
         self._stream_buffers()
         if wait:
             self._ahead.wait_primed()
         return self._ahead
-
-    def _broadcast_draw(self, ahead, c, rank):
-        """row-sharded streaming: the owner rank of chain c (c % world) draws (L, p0, u) from the
-        chain's RandomState(seed + c) and broadcasts them over NCCL; returns (L, u, p0 on device)"""
-        import torch
-        import torch.distributed as dist
-
-        M, dev = self.model.M, self.model.Aw_pad.device
-        if getattr(self, "_bc", None) is None:
-            self._bc = [torch.zeros(M + 2, dtype=torch.float64, device=dev) for _ in range(4)]
-            self._bc_host = torch.zeros(M + 2, dtype=torch.float64).pin_memory()
-            self._bc_i = 0
-        buf = self._bc[self._bc_i % 4]       # the device copy out of it is queued before reuse
-        self._bc_i += 1
-        if self._owner[c] == rank:
-            L, p0, u = ahead.take(c)
-            h = self._bc_host.numpy()
-            h[:M], h[M], h[M + 1] = p0, L, u
-            buf.copy_(self._bc_host, non_blocking=True)
-        dist.broadcast(buf, src=self._owner[c], group=self.model.group)
-        Lu = buf[M:].cpu().numpy()           # 16 bytes; also orders the pinned staging buffer
-        return int(Lu[0]), float(Lu[1]), buf[:M]
 
     def _stream_buffers(self):
         """record array + pinned staging for the positions that come back with every record"""
@@ -478,32 +631,54 @@ class HMCBatch:
         nrec, ndone = C.c_int32(), C.c_int32()
         count, fed, inflight = [0] * nc, [0] * nc, [0] * nc
         live = [True] * nc           # still needs accepted samples
-        ahead = self._ahead or self.start_draws()
+        ahead = self._ahead or self.start_draws(limit=max_proposals)
         self._ahead = None
+        if max_proposals is not None:
+            ahead.limit = max_proposals if ahead.limit is None else min(ahead.limit, max_proposals)
+        stager = _Stager(ahead.ring, nc, M, self.model.Aw_pad.device)
+        stager.start()
+        requested = [0] * nc
+
+        def top_up(c):
+            # keep two proposals staged on the device beyond the two the handle may hold
+            while live[c] and requested[c] < fed[c] + 4 and \
+                    (max_proposals is None or requested[c] < max_proposals):
+                stager.request(c)
+                requested[c] += 1
+
+        for k in range(4):  # proposal-major, so that every chain's first draws are staged first
+            for c in range(nc):
+                if requested[c] == k and (max_proposals is None or k < max_proposals):
+                    stager.request(c)
+                    requested[c] += 1
         _lib.check(lib.gi_hmcb_stream_begin(self._h, float(self.dt)), "gi_hmcb_stream_begin")
         self.stream_steps = 0
+        import time as _time
+        prof = self.stream_profile = dict(feed=0.0, advance=0.0, records=0.0, calls=0)
         try:
             while True:
+                _t0 = _time.perf_counter()
                 for c in range(nc):
                     while live[c] and inflight[c] < 2 and (max_proposals is None or fed[c] < max_proposals):
-                        if world > 1:
-                            L, u, p0d = self._broadcast_draw(ahead, c, rank)
-                            _lib.check(lib.gi_hmcb_stream_feed_dev(self._h, c, L, u, _lib.ptr(p0d)),
-                                       "gi_hmcb_stream_feed_dev")
-                        else:
-                            L, p0, u = ahead.take(c)
-                            _lib.check(lib.gi_hmcb_stream_feed(self._h, c, L, u, _lib.ptr(p0)),
-                                       "gi_hmcb_stream_feed")
+                        L, u, p0d = stager.take(c)  # staged on the device by the side stream
+                        _lib.check(lib.gi_hmcb_stream_feed_dev(self._h, c, L, u, _lib.ptr(p0d)),
+                                   "gi_hmcb_stream_feed_dev")
                         inflight[c] += 1
                         fed[c] += 1
+                        top_up(c)
                 run = C.c_int32()
                 _lib.check(lib.gi_hmcb_stream_runway(self._h, C.byref(run)), "gi_hmcb_stream_runway")
                 if run.value == 0:
                     break
+                _t1 = _time.perf_counter()
                 _lib.check(lib.gi_hmcb_stream_advance(self._h, run.value, recs, cap, C.byref(nrec),
                                                       C.byref(ndone), _lib.ptr(xh) if keep_x else None),
                            "gi_hmcb_stream_advance")
                 self.stream_steps += ndone.value
+                _t2 = _time.perf_counter()
+                prof["feed"] += _t1 - _t0
+                prof["advance"] += _t2 - _t1
+                prof["calls"] += 1
                 for i in range(nrec.value):
                     r = recs[i]
                     c = r.chain
@@ -529,7 +704,6 @@ class HMCBatch:
                         count[c] += 1
                         if count[c] >= target:
                             live[c] = False
-                            ahead.disable(c)
                     if on_record is not None:
                         on_record(c, r, acc)
                     if not self.quiet:
@@ -540,9 +714,18 @@ class HMCBatch:
                         sys.stdout.flush()
                     if max_proposals is not None and len(self.proposals[c]) >= max_proposals:
                         live[c] = False
-                        ahead.disable(c)
+                prof["records"] += _time.perf_counter() - _t2
         finally:
+            # the stager finishes the requests already queued (the same sequence on every rank, so
+            # its broadcasts pair up) before the RNG workers are stopped
+            stager.stop()
+            stager.join(timeout=120)
             ahead.stop()
+            if world > 1:
+                import torch.distributed as dist
+
+                dist.barrier(group=self.model.group)  # nobody unmaps while another rank still reads
+            ahead.ring.close()
         if not keep_x:  # the device's current positions, once (a chain may have run a queued
             # proposal past its target; the recorded statistics are gated and unaffected)
             _lib.check(lib.gi_hmcb_get_state(self._h, _lib.ptr(self.x), None, None), "gi_hmcb_get_state")

@@ -18,8 +18,13 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    import faulthandler
+
     import torch
     import torch.distributed as dist
+
+    # a hang must not outlive the caller's patience: dump every thread's stack and exit
+    faulthandler.dump_traceback_later(int(os.environ.get("GI_CHECK_TIMEOUT", "240")), exit=True)
 
     from gravinv3dhmc_b200.inversion import batched, hmc, potential
     from oracle import oracle_np as onp
