@@ -67,6 +67,8 @@ SIGNATURES = {
     "gi_prism_gz_assemble_grid": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, C.c_int32, C.c_int32,
                                             C.c_int32, _P, _I64, _D, _P, _I64, _P]),
     "gi_prism_field_assemble": (C.c_int, [C.c_int32, _P, _P, _P, _I64, _P, _I64, _D, _P, _P, _I64, _P]),
+    "gi_tess_field_assemble": (C.c_int, [C.c_int32, _P, _P, _P, _P, _I64, _P, _I64, _D, _D, _D, _P, _I64,
+                                          _P, _P]),
     "gi_tess_gz_assemble": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _D, _D, _D, _P, _I64, _P, _P]),
     "gi_tess_gz_leafcount": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I64, _D, _P, _I64, _P, _P]),
     "gi_colsumsq": (C.c_int, [_P, _I64, _I64, _I64, _P, C.c_int, _P]),

@@ -136,6 +136,15 @@ int gi_prism_field_assemble(int32_t field, const double *xp_dev, const double *y
                             const double *zp_dev, int64_t nrows, const double *bounds_dev, int64_t M,
                             double scale, const double *vec3_host, double *G_dev, int64_t ld,
                             void *stream);
+/* Tesseroid fields other than gz (GI_FIELD_POTENTIAL .. GI_FIELD_GZZ): the GLQ kernels of
+ * gravmag/_tesseroid_numba.py:160-328 through the same adaptive engine (:25-157) as
+ * gi_tess_gz_assemble; `ratio` is the distance-size ratio of gravmag/tesseroid.py:76-78 (1 / 1.6 / 8),
+ * G = (raw * scale1) * scale2 as in tesseroid.py:375-507 (pass scale2 = 1 for a single factor).
+ * Also serves gravmag/tesseroidforward.py (forward result = G @ density). */
+int gi_tess_field_assemble(int32_t field, const double *lon_dev, const double *sinlat_dev,
+                           const double *coslat_dev, const double *radius_dev, int64_t nrows,
+                           const double *bounds_dev, int64_t M, double ratio, double scale1,
+                           double scale2, double *G_dev, int64_t ld, int32_t *status_dev, void *stream);
 
 /* ---- sensitivity weighting (potential.py:232-264) ---------------------------------------- */
 /* out[c] (+)= sum_l G[l][c]^2, rows summed sequentially in row order. */

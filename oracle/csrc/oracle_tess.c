@@ -83,13 +83,58 @@ static double kernelz(double lon, double coslat, double sinlat, double radius,
     return result;
 }
 
+/* The other GLQ kernels, gravmag/_tesseroid_numba.py:160-328 (kernelV, kernelx, kernely, kernelxx,
+ * kernelxy, kernelxz, kernelyy, kernelyz, kernelzz), in numba's evaluation order. */
+enum { TF_POT = 0, TF_GX, TF_GY, TF_GZ, TF_GXX, TF_GXY, TF_GXZ, TF_GYY, TF_GYZ, TF_GZZ };
+
+static double kernel_field(int field, double lon, double coslat, double sinlat, double radius,
+                           const double *lonc, const double *sinlatc, const double *coslatc,
+                           const double *rc)
+{
+    if (field == TF_GZ)
+        return kernelz(lon, coslat, sinlat, radius, lonc, sinlatc, coslatc, rc);
+    double r_sqr = radius * radius;
+    double result = 0;
+    for (int i = 0; i < 2; ++i) {
+        double coslon = cos(lon - lonc[i]);
+        double sinlon = sin(lonc[i] - lon);
+        for (int j = 0; j < 2; ++j) {
+            double kphi = coslat * sinlatc[j] - sinlat * coslatc[j] * coslon;
+            double cospsi = sinlat * sinlatc[j] + coslat * coslatc[j] * coslon;
+            for (int k = 0; k < 2; ++k) {
+                double rc_sqr = rc[k] * rc[k];
+                double l_sqr = r_sqr + rc_sqr - 2 * radius * rc[k] * cospsi;
+                double kappa = rc_sqr * coslatc[j];
+                double deltay = rc[k] * coslatc[j] * sinlon;
+                double deltaz = rc[k] * cospsi - radius;
+                switch (field) {
+                case TF_POT: result += kappa / sqrt(l_sqr); break;
+                case TF_GX: result += kappa * rc[k] * kphi / pow(l_sqr, 1.5); break;
+                case TF_GY: result += kappa * (rc[k] * coslatc[j] * sinlon / pow(l_sqr, 1.5)); break;
+                case TF_GXX: {
+                    double t = rc[k] * kphi;
+                    result += kappa * (3 * (t * t) - l_sqr) / pow(l_sqr, 2.5);
+                    break;
+                }
+                case TF_GXY: result += kappa * 3 * rc_sqr * kphi * coslatc[j] * sinlon / pow(l_sqr, 2.5); break;
+                case TF_GXZ: result += kappa * 3 * rc[k] * kphi * deltaz / pow(l_sqr, 2.5); break;
+                case TF_GYY: result += kappa * (3 * (deltay * deltay) - l_sqr) / pow(l_sqr, 2.5); break;
+                case TF_GYZ: result += kappa * 3. * deltay * deltaz / pow(l_sqr, 2.5); break;
+                default: result += kappa * (3 * (deltaz * deltaz) - l_sqr) / pow(l_sqr, 2.5); break;
+                }
+            }
+        }
+    }
+    return result;
+}
+
 /* One (observation, tesseroid) pair, raw (unscaled) kernel value.
  * *err accumulates the reference's error_code (-1 per refused split);
  * returns NaN and sets *overflow=1 where the reference raises OverflowError.
  * stats (optional): [0] += leaves evaluated, [1] = max(stack depth).  */
-double oracle_tess_gz_pair(double lon, double sinlat, double coslat, double radius,
-                           const double *bounds, double ratio, int *err, int *overflow,
-                           int64_t *stats)
+double oracle_tess_field_pair(int field, double lon, double sinlat, double coslat, double radius,
+                              const double *bounds, double ratio, int *err, int *overflow,
+                              int64_t *stats)
 {
     double stack[STACK_SIZE][6];
     double lonc[2], sinlatc[2], coslatc[2], rc[2];
@@ -150,12 +195,41 @@ double oracle_tess_gz_pair(double lon, double sinlat, double coslat, double radi
                 stats[1] = stktop + 1;
         } else {
             double scale = scale_nodes(w, e, s, n, top, bottom, lonc, sinlatc, coslatc, rc);
-            acc += scale * kernelz(lon, coslat, sinlat, radius, lonc, sinlatc, coslatc, rc);
+            acc += scale * kernel_field(field, lon, coslat, sinlat, radius, lonc, sinlatc, coslatc, rc);
             if (stats)
                 stats[0] += 1;
         }
     }
     return acc;
+}
+
+double oracle_tess_gz_pair(double lon, double sinlat, double coslat, double radius,
+                           const double *bounds, double ratio, int *err, int *overflow,
+                           int64_t *stats)
+{
+    return oracle_tess_field_pair(TF_GZ, lon, sinlat, coslat, radius, bounds, ratio, err, overflow, stats);
+}
+
+/* kernel2d for any field (gravmag/tesseroid.py:324-510); dens (optional, [M]) also accumulates the
+ * forward result res[l] += density * scale * kernel in the reference's order
+ * (_tesseroid_numba.py:62-64), scaled like kernel2d. */
+int oracle_tess_field(int field, const double *lon, const double *sinlat, const double *coslat,
+                      const double *radius, int64_t N, const double *bounds, int64_t M, double ratio,
+                      double scale1, double scale2, double *kernel2d, int64_t ld, const double *dens,
+                      double *res, int *overflow)
+{
+    int err = 0;
+    if (field < TF_POT || field > TF_GZZ) return -9999;
+    for (int64_t c = 0; c < M; ++c)
+        for (int64_t l = 0; l < N; ++l) {
+            double v = oracle_tess_field_pair(field, lon[l], sinlat[l], coslat[l], radius[l],
+                                              bounds + 6 * c, ratio, &err, overflow, NULL);
+            if (kernel2d) kernel2d[l * ld + c] = v * scale1 * scale2;
+            if (dens && res) res[l] += dens[c] * v;
+        }
+    if (dens && res)
+        for (int64_t l = 0; l < N; ++l) res[l] = res[l] * scale1 * scale2;
+    return err;
 }
 
 /* kernel2d[N][ld] row-major for M active tesseroids, bounds[M][6] = w,e,s,n,top,bottom.

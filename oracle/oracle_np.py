@@ -72,6 +72,10 @@ def _lib():
         L.oracle_tess_leaves.argtypes = [dp, dp, dp, dp, i64, dp, i64, ctypes.c_double,
                                          ctypes.c_void_p, i64]
         L.oracle_tess_leaves.restype = ctypes.c_int
+        L.oracle_tess_field.argtypes = [ctypes.c_int, dp, dp, dp, dp, i64, dp, i64, ctypes.c_double,
+                                        ctypes.c_double, ctypes.c_double, dp, i64, dp, dp,
+                                        ctypes.POINTER(ctypes.c_int)]
+        L.oracle_tess_field.restype = ctypes.c_int
         L.oracle_prism_field.argtypes = [ctypes.c_int, dp, dp, dp, i64, dp, i64, ctypes.c_double, dp,
                                          dp, i64, dp, ctypes.c_int, dp]
         L.oracle_prism_field.restype = ctypes.c_int
@@ -213,6 +217,61 @@ def tess_gz(lon, lat, height, bounds, ratio=RATIO_G, threads: int = 1, stats=Non
     if any(ovfs):
         raise OverflowError
     return K, int(sum(errs))
+
+
+TESS_FIELDS = {"potential": 0, "geoid": 0, "gx": 1, "gy": 2, "gz": 3, "gxx": 4, "gxy": 5, "gxz": 6,
+               "gyy": 7, "gyz": 8, "gzz": 9}
+RATIO_V, RATIO_GG = 1, 8  # gravmag/tesseroid.py:76,78
+G_SPHERICAL_S = 0.00000000006673  # constants.py:33 "Gs"
+
+
+def tess_field_scales(field, forward=False):
+    """(ratio, scale1, scale2) of gravmag/tesseroid.py:324-510 -- `kernel2d*SI2MGAL*G` is two
+    multiplications, `kernel2d *= G` one; gy is scaled with Gs (tesseroid.py:416-417) -- and of
+    gravmag/tesseroidforward.py:236-788 (`result *= SI2MGAL*G`: one multiplication by the product,
+    gy with G)."""
+    if field in ("potential", "geoid"):
+        return RATIO_V, (G if field == "potential" else G / 9.80), 1.0
+    unit, ratio = (SI2MGAL, RATIO_G) if field in ("gx", "gy", "gz") else (SI2EOTVOS, RATIO_GG)
+    if forward:
+        return ratio, unit * G, 1.0
+    return ratio, unit, (G_SPHERICAL_S if field == "gy" else G)
+
+
+def tess_field(field, lon, lat, height, bounds, dens=None, ratio=None, forward=False, threads: int = 1):
+    """(result, kernel2d, error_code) of gravmag/tesseroid.py's `potential, geoid, gx .. gzz`
+    (:324-510), or with forward=True the result of gravmag/tesseroidforward.py's functions
+    (kernel2d = None), for an explicit bounds table."""
+    lon, lat, height = _c(lon), _c(lat), _c(height)
+    assert lon.shape == lat.shape == height.shape, "Input coordinate arrays must have same shape"
+    r0, s1, s2 = tess_field_scales(field, forward)
+    ratio = r0 if ratio is None else ratio
+    assert ratio > 0
+    bounds = _c(bounds).reshape(-1, 6)
+    lonr, sinlat, coslat, radius = (_c(a) for a in convert_coords(lon, lat, height))
+    N, M = lon.shape[0], bounds.shape[0]
+    K = None if forward else np.zeros((N, M))
+    res = np.zeros(N)
+    d = None if dens is None else _c(dens)
+    L = _lib()
+    errs, ovfs = [], []
+
+    def run(lo, hi):
+        if hi <= lo:
+            return
+        ovf = ctypes.c_int(0)
+        e = L.oracle_tess_field(TESS_FIELDS[field], _dp(lonr[lo:hi]), _dp(sinlat[lo:hi]),
+                                _dp(coslat[lo:hi]), _dp(radius[lo:hi]), hi - lo, _dp(bounds), M, ratio,
+                                s1, s2, None if K is None else _dp(K[lo:hi]), M,
+                                None if d is None else _dp(d), None if d is None else _dp(res[lo:hi]),
+                                ctypes.byref(ovf))
+        errs.append(e)
+        ovfs.append(ovf.value)
+
+    _run_rows(run, N, threads)
+    if any(ovfs):
+        raise OverflowError
+    return res, K, int(sum(errs))
 
 
 def tess_leaves(lon, lat, height, bounds, ratio=RATIO_G, threads: int = 1):
