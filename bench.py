@@ -427,7 +427,9 @@ def gpu_arm(args):
 
     # ---- e2e: the public per-proposal call with host buffers (momentum in, state out) ----
     e2e = None
-    if nch > 1:
+    if args.no_e2e:
+        pass
+    elif nch > 1:
         # public batched call: per proposal the host draws L, p0 (randn) and u for every chain in the
         # reference's RNG order, p0 goes host->device, accepted states come back device->host
         bt.start_draws(wait=True)  # the first two proposals' random numbers are ready up front
@@ -592,6 +594,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=128, help="observation rows of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8, help="leapfrog steps per CPU chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="profiling runs (ncu): skip the end-to-end arm, keep the device-timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = reference_arm(args) if args.impl == "reference" else gpu_arm(args)

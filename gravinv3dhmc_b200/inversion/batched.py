@@ -573,8 +573,17 @@ class HMCBatch:
             # rank 0 creates the ring file, the others map it (collective: every rank gets here)
             name = [None]
             if rank == 0:
-                fd, name[0] = tempfile.mkstemp(prefix="gi_draws_",
-                                               dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+                # /dev/shm when it has room for the ring (plus slack), else the temp directory (a
+                # page-cache backed file: same semantics, the kernel may write it back lazily)
+                need = 8 * nc * 3 * (M + 2) + (64 << 20)
+                base = None
+                try:
+                    st = os.statvfs("/dev/shm")
+                    if st.f_bavail * st.f_frsize > need:
+                        base = "/dev/shm"
+                except OSError:
+                    pass
+                fd, name[0] = tempfile.mkstemp(prefix="gi_draws_", dir=base)
                 os.close(fd)
                 ring = _DrawRing(nc, M, world, rank, path=name[0], create=True)
             dist.broadcast_object_list(name, src=0, group=self.model.group)
