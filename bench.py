@@ -239,7 +239,7 @@ def gpu_arm(args):
         (nz, ny, nx), _, side = WORKLOADS[wl]
         N, M = side * side, nz * ny * nx
         lo, hi = potential.split_rows(N, world)[rank]
-        need = (hi - lo) * _lib.padded_ld(M) * 8 + 12 * _lib.padded_ld(M) * 8 * max(args.chains, 8)
+        need = (hi - lo) * _lib.padded_ld(M) * 8 + 26 * _lib.padded_ld(M) * 8 * max(args.chains, 8)
         fits = torch.tensor([1.0 if need < free - (2 << 30) else 0.0], device=dev)
         if world > 1:
             dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)

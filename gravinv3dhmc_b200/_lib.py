@@ -52,6 +52,7 @@ class CgConfig(C.Structure):
 
 
 CG_REGINV, CG_BOOTSTRAP = 0, 1
+STREAM_QUEUE_DEPTH = 4  # GI_STREAM_QUEUE_DEPTH
 
 _P = C.c_void_p
 _I64 = C.c_int64

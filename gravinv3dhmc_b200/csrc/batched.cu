@@ -470,7 +470,7 @@ struct BatchCtl {
     int32_t use_modes;
     signed char modes[64];
     signed char slots[64];
-    const double *qp;      // [2][C][ld] momentum queue
+    const double *qp;      // [GI_STREAM_QUEUE_DEPTH][C][ld] momentum queue
     int64_t qp_slot_stride;
 };
 
@@ -894,13 +894,13 @@ struct gi_hmcb {
     // streaming sampler
     struct ChainQ {
         int L_cur, pos, qn, qhead;
-        int qL[2];
-        double qu[2];
+        int qL[GI_STREAM_QUEUE_DEPTH];
+        double qu[GI_STREAM_QUEUE_DEPTH];
         int64_t seq;
     } cq[64];
     bool streaming;
     double stream_dt;
-    double *qp;  // [2][C][ld] queued momentum draws
+    double *qp;  // [GI_STREAM_QUEUE_DEPTH][C][ld] queued momentum draws
     gi_stream_record *rec_dev, *rec_host;
     int64_t rec_cap;
     double *s_xin, *s_xout, *s_mwin, *s_mwout;
@@ -1340,7 +1340,7 @@ extern "C" int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t 
 extern "C" int gi_hmcb_stream_begin(gi_hmcb *h, double dt) {
     GI_REQUIRE(h, "gi_hmcb_stream_begin: null handle");
     GI_REQUIRE(h->has_state, "gi_hmcb_stream_begin: call gi_hmcb_set_state first");
-    const size_t bq = sizeof(double) * 2 * h->C * h->cfg.ld;
+    const size_t bq = sizeof(double) * GI_STREAM_QUEUE_DEPTH * h->C * h->cfg.ld;
     if (!h->qp) {
         GI_CUDA(cudaMalloc(&h->qp, bq));
         GI_CUDA(cudaMemsetAsync(h->qp, 0, bq, h->stream));
@@ -1368,11 +1368,11 @@ static int stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u, const dou
     GI_REQUIRE(h && h->streaming && p0, "gi_hmcb_stream_feed: call gi_hmcb_stream_begin first");
     GI_REQUIRE(chain >= 0 && chain < h->nchains && L >= 1, "gi_hmcb_stream_feed: bad chain or L");
     gi_hmcb::ChainQ &q = h->cq[chain];
-    if (q.qn >= 2) {
-        set_error("gi_hmcb_stream_feed: chain %d already has two proposals queued", chain);
+    if (q.qn >= GI_STREAM_QUEUE_DEPTH) {
+        set_error("gi_hmcb_stream_feed: chain %d already has %d proposals queued", chain, GI_STREAM_QUEUE_DEPTH);
         return GI_ERR_BUSY;
     }
-    const int slot = (q.qhead + q.qn) & 1;
+    const int slot = (q.qhead + q.qn) % GI_STREAM_QUEUE_DEPTH;
     // same stream as the kernels: the copy is ordered after the step that consumed this slot
     GI_CUDA(cudaMemcpyAsync(h->qp + ((int64_t)slot * h->C + chain) * h->cfg.ld, p0,
                             sizeof(double) * h->cfg.M, kind, h->stream));
@@ -1399,7 +1399,7 @@ extern "C" int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps) {
         const gi_hmcb::ChainQ &q = h->cq[c];
         if (q.L_cur == 0 && q.qn == 0) continue;  // parked chain
         int rem = q.L_cur > 0 ? q.L_cur - q.pos : 0;
-        for (int k = 0; k < q.qn; ++k) rem += q.qL[(q.qhead + k) & 1];
+        for (int k = 0; k < q.qn; ++k) rem += q.qL[(q.qhead + k) % GI_STREAM_QUEUE_DEPTH];
         if (best < 0 || rem < best) best = rem;
     }
     *steps = best < 0 ? 0 : best;
@@ -1544,7 +1544,7 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
                 q.L_cur = q.qL[q.qhead];
                 q.pos = 0;
                 q.qn -= 1;
-                q.qhead ^= 1;
+                q.qhead = (q.qhead + 1) % GI_STREAM_QUEUE_DEPTH;
             }
         }
         std::swap(h->s_xin, h->s_xout);

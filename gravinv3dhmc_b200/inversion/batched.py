@@ -289,7 +289,7 @@ class _Stager(threading.Thread):
     copy on its own stream: the host-side exchange and the host->device transfer overlap the
     contractions already queued."""
 
-    SLOTS = 4  # per chain: two proposals queued in the handle + two staged
+    SLOTS = _lib.STREAM_QUEUE_DEPTH + 2  # per chain: the handle's queue + two staged beyond it
 
     def __init__(self, ring, nchains, M, dev):
         super().__init__(daemon=True)
@@ -646,16 +646,20 @@ class HMCBatch:
             ahead.limit = max_proposals if ahead.limit is None else min(ahead.limit, max_proposals)
         stager = _Stager(ahead.ring, nc, M, self.model.Aw_pad.device)
         stager.start()
-        requested = [0] * nc
+        requested, finished = [0] * nc, [0] * nc
+        depth = _lib.STREAM_QUEUE_DEPTH
 
         def top_up(c):
-            # keep two proposals staged on the device beyond the two the handle may hold
-            while live[c] and requested[c] < fed[c] + 4 and \
+            # keep the handle's queue full and two more proposals staged beyond it.  A device slot is
+            # reused SLOTS proposals later: that one is requested only after the slot's previous
+            # occupant has FINISHED (its record was read back, so the device-to-device copy that fed
+            # it has long completed on the sampler's stream)
+            while live[c] and requested[c] < finished[c] + stager.SLOTS and \
                     (max_proposals is None or requested[c] < max_proposals):
                 stager.request(c)
                 requested[c] += 1
 
-        for k in range(4):  # proposal-major, so that every chain's first draws are staged first
+        for k in range(stager.SLOTS):  # proposal-major: every chain's first draws are staged first
             for c in range(nc):
                 if requested[c] == k and (max_proposals is None or k < max_proposals):
                     stager.request(c)
@@ -668,13 +672,12 @@ class HMCBatch:
             while True:
                 _t0 = _time.perf_counter()
                 for c in range(nc):
-                    while live[c] and inflight[c] < 2 and (max_proposals is None or fed[c] < max_proposals):
+                    while live[c] and inflight[c] < depth and (max_proposals is None or fed[c] < max_proposals):
                         L, u, p0d = stager.take(c)  # staged on the device by the side stream
                         _lib.check(lib.gi_hmcb_stream_feed_dev(self._h, c, L, u, _lib.ptr(p0d)),
                                    "gi_hmcb_stream_feed_dev")
                         inflight[c] += 1
                         fed[c] += 1
-                        top_up(c)
                 run = C.c_int32()
                 _lib.check(lib.gi_hmcb_stream_runway(self._h, C.byref(run)), "gi_hmcb_stream_runway")
                 if run.value == 0:
@@ -692,6 +695,8 @@ class HMCBatch:
                     r = recs[i]
                     c = r.chain
                     inflight[c] -= 1
+                    finished[c] += 1
+                    top_up(c)
                     if not live[c]:
                         continue  # a queued proposal that ran after the chain reached its target
                     acc = bool(r.accept)

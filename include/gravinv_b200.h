@@ -55,7 +55,8 @@ extern "C" {
 #define GI_ERR_CUDA (-2)     /* CUDA runtime error / no device */
 #define GI_ERR_OVERFLOW (-3) /* tesseroid subdivision stack overflow (OverflowError, _tesseroid_numba.py:53-54) */
 #define GI_ERR_NOMEM (-4)
-#define GI_ERR_BUSY (-5)     /* gi_hmcb_stream_feed: the chain already has two proposals queued */
+#define GI_ERR_BUSY (-5)     /* gi_hmcb_stream_feed: the chain's proposal queue is full */
+#define GI_STREAM_QUEUE_DEPTH 4 /* proposals a chain may have queued behind the running one */
 
 /* regularisers, inversion/potential.py:831-836 */
 #define GI_REG_DAMPING 0
@@ -335,10 +336,10 @@ int gi_hmcb_set_shard(gi_hmcb *h, int64_t n_total, const double *dobs_c_host, do
  * each gradient evaluation (one "batch step"), and a chain that ends a trajectory -- Metropolis test,
  * commit -- opens its next one inside the same step, so no chain idles while others finish longer
  * trajectories (hmc.py:295-300 per chain, with each chain's own L sequence).  The host feeds the draws
- * of up to two proposals per chain ahead of time (L, u = rand(), p0 = randn(M)*Sigma, in the
+ * of up to GI_STREAM_QUEUE_DEPTH proposals per chain ahead of time (L, u = rand(), p0 = randn(M)*Sigma, in the
  * reference's RNG order) and collects one record per finished proposal.
  *   begin    -- chains keep their current state (gi_hmcb_set_state); queues are emptied
- *   feed     -- enqueue one proposal for `chain`; GI_ERR_BUSY if two are already queued
+ *   feed     -- enqueue one proposal for `chain`; GI_ERR_BUSY if the chain's queue is full
  *   runway   -- batch steps that can run before some started/fed chain runs out of queued work
  *   advance  -- run up to nsteps batch steps (fewer if every chain runs dry or the record buffer
  *               fills); returns the records of the proposals that finished, in completion order;
