@@ -145,12 +145,14 @@ SIGNATURES = {
     "gi_hmcb_attach_stats": (C.c_int, [_P, _P, _P]),
     "gi_cg_create": (C.c_int, [C.POINTER(CgConfig), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "gi_cg_destroy": (C.c_int, [_P]),
+    "gi_cg_set_shard": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "gi_cg_run": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
     "gi_cg_get_result": (C.c_int, [_P, _P, _P, _P]),
     "gi_cg_launch_count": (_I64, [_P]),
 }
 
 SHARD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32)
+CG_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32)
 
 _LIB = None
 

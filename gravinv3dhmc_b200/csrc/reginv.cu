@@ -144,14 +144,17 @@ cg_dir_kernel(CgDims dm, int k, const double *__restrict__ I, double *__restrict
     column_reduce3(a0, a1, 0.0, blockpart, counter, s + S_IWI, s + S_IWIW, nullptr);
 }
 
-// one CTA per column over the N-vector Q = Aw Iw:  qq = sum w q^2 and the step length
-// kstep = Iw.I / (|Aw Iw|^2 + alpha |Iw|^2)   (reginv.py:425, 460)
+// one CTA per column over this rank's rows of Q = Aw Iw:  red[c] = sum w q^2  (summed over the row
+// shards by the caller's hook before cg_kstep_kernel)
 __global__ void __launch_bounds__(1024)
-cg_kstep_kernel(CgDims dm, const double *__restrict__ Q, const double *__restrict__ W, double *S) {
+cg_qq_kernel(CgDims dm, const double *__restrict__ Q, const double *__restrict__ W, const double *S,
+             double *__restrict__ red) {
     __shared__ double scratch[32];
     const int c = blockIdx.x;
-    double *s = S + (int64_t)c * S_STRIDE;
-    if (s[S_ACTIVE] == 0.0) return;
+    if (S[(int64_t)c * S_STRIDE + S_ACTIVE] == 0.0) {
+        if (threadIdx.x == 0) red[c] = 0.0;
+        return;
+    }
     const double *q = Q + (int64_t)c * dm.N;
     const double *w = W ? W + (int64_t)c * dm.N : nullptr;
     double acc = 0.0;
@@ -160,11 +163,18 @@ cg_kstep_kernel(CgDims dm, const double *__restrict__ Q, const double *__restric
         acc += w ? w[l] * v * v : v * v;
     }
     acc = block_sum(acc, scratch);
-    if (threadIdx.x == 0) {
-        s[S_QQ] = acc;
-        const double den = __dadd_rn(norm_sq(acc), __dmul_rn(s[S_ALPHA], norm_sq(s[S_IWIW])));
-        s[S_KSTEP] = s[S_IWI] / den;
-    }
+    if (threadIdx.x == 0) red[c] = acc;
+}
+
+// the step length  kstep = Iw.I / (|Aw Iw|^2 + alpha |Iw|^2)   (reginv.py:425, 460)
+__global__ void cg_kstep_kernel(int C, const double *__restrict__ red, double *S) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double *s = S + (int64_t)c * S_STRIDE;
+    if (s[S_ACTIVE] == 0.0) return;
+    s[S_QQ] = red[c];
+    const double den = __dadd_rn(norm_sq(red[c]), __dmul_rn(s[S_ALPHA], norm_sq(s[S_IWIW])));
+    s[S_KSTEP] = s[S_IWI] / den;
 }
 
 // mw_new = Wm clamp(WmInv (mw - kstep Iw), rhomin, rhomax)   (reginv.py:427-432, 462-467)
@@ -260,19 +270,18 @@ cg_model_kernel(CgDims dm, const double *__restrict__ mw, const double *__restri
     column_reduce3(um, 0.0, 0.0, blockpart, counter, s + S_MODEL_NEW, nullptr, nullptr);
 }
 
-// one CTA per column over D = Aw mw:  r = d - dobs, R = w r (input of the adjoint), data = |r|_w^2,
-// bookkeeping of the iteration (reginv.py:469-488 / 692-702):
-//   k < 0  : start point -- data_cur = data_new = data(mw0); the REGINV variant records entry 0
-//   REGINV : record data/N, model/M at index k, then stop the column when data/N < tol
-//   BOOT   : stop the column when data < tol BEFORE recording; records go to index k-1
+// one CTA per column over this rank's rows of D = Aw mw:  r = d - dobs, R = w r (input of the
+// adjoint), red[c] = sum w r^2  (summed over the row shards by the caller's hook before cg_book_kernel)
 __global__ void __launch_bounds__(1024)
-cg_resid_kernel(CgDims dm, int k, int maxk, double tol, const double *__restrict__ D,
-                const double *__restrict__ dobs, const double *__restrict__ W, double *__restrict__ R,
-                double *S, double *hist_data, double *hist_model, int *nactive) {
+cg_resid_kernel(CgDims dm, const double *__restrict__ D, const double *__restrict__ dobs,
+                const double *__restrict__ W, double *__restrict__ R, const double *S,
+                double *__restrict__ red) {
     __shared__ double scratch[32];
     const int c = blockIdx.x;
-    double *s = S + (int64_t)c * S_STRIDE;
-    if (s[S_ACTIVE] == 0.0) return;
+    if (S[(int64_t)c * S_STRIDE + S_ACTIVE] == 0.0) {
+        if (threadIdx.x == 0) red[c] = 0.0;
+        return;
+    }
     const double *d = D + (int64_t)c * dm.N;
     const double *w = W ? W + (int64_t)c * dm.N : nullptr;
     double *r = R + (int64_t)c * dm.npad;
@@ -287,14 +296,28 @@ cg_resid_kernel(CgDims dm, int k, int maxk, double tol, const double *__restrict
         acc += wr * rr;
     }
     acc = block_sum(acc, scratch);
-    if (threadIdx.x != 0) return;
-    const double data = norm_sq(acc);
+    if (threadIdx.x == 0) red[c] = acc;
+}
+
+// bookkeeping of the iteration from the (global) data term (reginv.py:469-488 / 692-702), one
+// thread per column; n_total = observations over all row shards:
+//   k < 0  : start point -- data_cur = data_new = data(mw0); the REGINV variant records entry 0
+//   REGINV : record data/N, model/M at index k, then stop the column when data/N < tol
+//   BOOT   : stop the column when data < tol BEFORE recording; records go to index k-1
+__global__ void cg_book_kernel(CgDims dm, int k, int maxk, double tol, int64_t n_total,
+                               const double *__restrict__ red, double *S, double *hist_data,
+                               double *hist_model, int *nactive) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= dm.C) return;
+    double *s = S + (int64_t)c * S_STRIDE;
+    if (s[S_ACTIVE] == 0.0) return;
+    const double data = norm_sq(red[c]);
     s[S_DATA_NEW] = data;
     const bool boot = dm.variant == GI_CG_BOOTSTRAP;
     if (k < 0) {
         s[S_DATA_CUR] = data;
         if (!boot) {
-            hist_data[(int64_t)c * maxk] = data / (double)dm.N;
+            hist_data[(int64_t)c * maxk] = data / (double)n_total;
             hist_model[(int64_t)c * maxk] = s[S_MODEL_NEW] / (double)dm.M;
         }
         return;
@@ -305,13 +328,13 @@ cg_resid_kernel(CgDims dm, int k, int maxk, double tol, const double *__restrict
     if (boot) {
         stop = data < tol;
         if (!stop) {
-            hist_data[(int64_t)c * maxk + k - 1] = data / (double)dm.N;
+            hist_data[(int64_t)c * maxk + k - 1] = data / (double)n_total;
             hist_model[(int64_t)c * maxk + k - 1] = s[S_MODEL_NEW] / (double)dm.M;
         }
     } else {
-        hist_data[(int64_t)c * maxk + k] = data / (double)dm.N;
+        hist_data[(int64_t)c * maxk + k] = data / (double)n_total;
         hist_model[(int64_t)c * maxk + k] = s[S_MODEL_NEW] / (double)dm.M;
-        stop = data / (double)dm.N < tol;
+        stop = data / (double)n_total < tol;
     }
     if (stop) {
         s[S_ACTIVE] = 0.0;
@@ -365,7 +388,22 @@ struct gi_cg {
     int *nactive_dev, *nactive_host;
     int32_t hist_maxk;
     int64_t launches;
+    // row-sharded mode (gi_cg_set_shard): caller-owned reduction buffers + sum-reduce hook
+    int64_t n_total;
+    double *red, *gt_ext;  // [C] scalars; [C][ld] adjoint output
+    double *red_own;
+    gi_cg_hook hook;
+    void *hook_user;
 };
+
+static int cg_reduce(gi_cg *h, int what) {
+    if (!h->hook) return GI_OK;
+    if (h->hook(h->hook_user, what)) {
+        set_error("gi_cg: the reduction hook failed");
+        return GI_ERR_CUDA;
+    }
+    return GI_OK;
+}
 
 static void cg_free(gi_cg *h) {
     if (!h) return;
@@ -375,6 +413,7 @@ static void cg_free(gi_cg *h) {
     for (double *b : bufs) cudaFree(b);
     cudaFree(h->counter);
     cudaFree(h->nactive_dev);
+    cudaFree(h->red_own);
     if (h->nactive_host) cudaFreeHost(h->nactive_host);
     delete h;
 }
@@ -421,6 +460,9 @@ extern "C" int gi_cg_create(const gi_cg_config *cfg, const double *G_dev, const 
     alloc(&h->S, sizeof(double) * C * S_STRIDE);
     alloc(&h->blockpart, sizeof(double) * 3 * C * h->vblocks);
     alloc(&h->v0, sizeof(double) * cfg->ld);
+    alloc(&h->red_own, sizeof(double) * C);
+    h->red = h->red_own;
+    h->n_total = cfg->N;
     if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int) * C);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * C, h->s);
     if (e == cudaSuccess) e = cudaMalloc(&h->nactive_dev, sizeof(int));
@@ -439,6 +481,17 @@ extern "C" int gi_cg_create(const gi_cg_config *cfg, const double *G_dev, const 
     return GI_OK;
 }
 
+extern "C" int gi_cg_set_shard(gi_cg *h, int64_t n_total, double *gt_dev, double *red_dev, gi_cg_hook hook,
+                               void *user) {
+    GI_REQUIRE(h && n_total >= h->cfg.N && gt_dev && red_dev && hook, "gi_cg_set_shard: bad argument");
+    h->n_total = n_total;
+    h->gt_ext = gt_dev;
+    h->red = red_dev;
+    h->hook = hook;
+    h->hook_user = user;
+    return GI_OK;
+}
+
 extern "C" int gi_cg_destroy(gi_cg *h) {
     cg_free(h);
     return GI_OK;
@@ -451,10 +504,13 @@ static int cg_forward(gi_cg *h, const double *X) {
     return gi_gemm_fwd(h->plan, h->G, X, h->D, h->s);
 }
 
+// Gt = Aw^T R, summed over the row shards
 static int cg_adjoint(gi_cg *h) {
-    if (h->cfg.ncols == 1) { h->launches += 2; return gi_gemv_adj(h->plan, h->G, h->R, h->Gt, h->s); }
-    h->launches += 1;
-    return gi_gemm_adj(h->plan, h->G, h->R, h->Gt, h->s);
+    double *gt = h->gt_ext ? h->gt_ext : h->Gt;
+    int rc;
+    if (h->cfg.ncols == 1) { h->launches += 2; rc = gi_gemv_adj(h->plan, h->G, h->R, gt, h->s); }
+    else { h->launches += 1; rc = gi_gemm_adj(h->plan, h->G, h->R, gt, h->s); }
+    return rc ? rc : cg_reduce(h, 0);
 }
 
 static int cg_model(gi_cg *h) {
@@ -468,10 +524,14 @@ static int cg_model(gi_cg *h) {
 
 static int cg_resid(gi_cg *h, int k, int maxk) {
     double *hd = h->hist + (int64_t)h->dm.C * maxk, *hm = h->hist + 2 * (int64_t)h->dm.C * maxk;
-    cg_resid_kernel<<<h->dm.C, 1024, 0, h->s>>>(h->dm, k, maxk, h->cfg.stop_tol, h->D, h->dobs, h->W, h->R,
-                                               h->S, hd, hm, h->nactive_dev);
+    cg_resid_kernel<<<h->dm.C, 1024, 0, h->s>>>(h->dm, h->D, h->dobs, h->W, h->R, h->S, h->red);
     GI_LAUNCH_CHECK();
-    h->launches += 1;
+    int rc = cg_reduce(h, 1);
+    if (rc) return rc;
+    cg_book_kernel<<<1, 64, 0, h->s>>>(h->dm, k, maxk, h->cfg.stop_tol, h->n_total, h->red, h->S, hd, hm,
+                                       h->nactive_dev);
+    GI_LAUNCH_CHECK();
+    h->launches += 2;
     return GI_OK;
 }
 
@@ -503,15 +563,19 @@ extern "C" int gi_cg_run(gi_cg *h, const double *mw0_host, int32_t maxk, int32_t
     for (int k = 0; k < maxk; ++k) {
         cg_alpha_kernel<<<1, 64, 0, s>>>(h->S, C, k, h->cfg.q, h->hist, maxk);
         if ((rc = cg_adjoint(h))) return rc;
-        cg_grad_kernel<<<vgrid, kVecThreads, 0, s>>>(dm, h->Gt, h->gR, h->I, h->S, h->blockpart, h->counter);
+        cg_grad_kernel<<<vgrid, kVecThreads, 0, s>>>(dm, h->gt_ext ? h->gt_ext : h->Gt, h->gR, h->I, h->S,
+                                                     h->blockpart, h->counter);
         cg_dir_kernel<<<vgrid, kVecThreads, 0, s>>>(dm, k, h->I, h->Iw, h->S, h->blockpart, h->counter);
         GI_LAUNCH_CHECK();
         if ((rc = cg_forward(h, h->Iw))) return rc;
-        cg_kstep_kernel<<<C, 1024, 0, s>>>(dm, h->D, h->W, h->S);
+        cg_qq_kernel<<<C, 1024, 0, s>>>(dm, h->D, h->W, h->S, h->red);
+        GI_LAUNCH_CHECK();
+        if ((rc = cg_reduce(h, 1))) return rc;
+        cg_kstep_kernel<<<1, 64, 0, s>>>(C, h->red, h->S);
         cg_step_kernel<<<vgrid, kVecThreads, 0, s>>>(dm, h->Iw, h->wm, h->wminv, h->cfg.rhomin, h->cfg.rhomax,
                                                     h->mw, h->S);
         GI_LAUNCH_CHECK();
-        h->launches += 5;
+        h->launches += 6;
         if ((rc = cg_model(h))) return rc;
         if ((rc = cg_forward(h, h->mw))) return rc;
         if ((rc = cg_resid(h, k, maxk))) return rc;

@@ -41,11 +41,14 @@ class _CgHandle:
     """RAII wrapper of a gi_cg handle."""
 
     def __init__(self, Aw_pad, M, dobs, wm, wminv, wmsq, variant, reg, q, tol, bounds, ncols=1,
-                 mwapr=None, weights=None):
-        self.torch = _lib.require_cuda()
+                 mwapr=None, weights=None, shard=None):
+        """`shard = (rows, n_total, group)`: Aw_pad / dobs / weights hold this rank's observation rows
+        `rows = (lo, hi)` of `n_total`; the partial sums are all-reduced over `group` (NCCL)."""
+        self.torch = torch = _lib.require_cuda()
         self.L = _lib.lib()
         n, ld = (int(v) for v in Aw_pad.shape)
         self.N, self.M, self.ncols = n, int(M), int(ncols)
+        self.shard = shard
         cfg = _lib.CgConfig(n, int(M), ld, int(ncols), int(variant), reg, float(q), float(tol),
                             float(bounds[0]), float(bounds[1]))
         self._keep = (Aw_pad, wm, wminv, wmsq)
@@ -56,6 +59,27 @@ class _CgHandle:
         _lib.check(self.L.gi_cg_create(C.byref(cfg), _lib.ptr(Aw_pad), _lib.ptr(dobs), _lib.ptr(wm),
                                        _lib.ptr(wminv), _lib.ptr(wmsq), _lib.ptr(apr), _lib.ptr(w),
                                        _lib.stream_ptr(), C.byref(self.h)), "gi_cg_create")
+        if shard is not None:
+            import torch.distributed as dist
+
+            _, n_total, group = shard
+            cp = 1 if ncols == 1 else (int(ncols) + 7) // 8 * 8
+            f64 = dict(dtype=torch.float64, device=Aw_pad.device)
+            self._gt, self._red = torch.zeros(cp * ld, **f64), torch.zeros(cp, **f64)
+
+            def hook(user, what):
+                try:
+                    dist.all_reduce(self._gt if what == 0 else self._red, op=dist.ReduceOp.SUM, group=group)
+                    return 0
+                except Exception:  # an exception must not unwind through the C frames
+                    import traceback
+
+                    traceback.print_exc()
+                    return -1
+
+            self._hook = _lib.CG_HOOK(hook)  # keep the callback object alive with the handle
+            _lib.check(self.L.gi_cg_set_shard(self.h, int(n_total), _lib.ptr(self._gt), _lib.ptr(self._red),
+                                              self._hook, None), "gi_cg_set_shard")
 
     def run(self, mw0, maxk):
         mw0 = np.ascontiguousarray(mw0, dtype=np.float64)
@@ -70,6 +94,13 @@ class _CgHandle:
         data = np.zeros((self.ncols, self.N)) if want_data else None
         _lib.check(self.L.gi_cg_get_result(self.h, _lib.ptr(model), _lib.ptr(data), None),
                    "gi_cg_get_result")
+        if data is not None and self.shard is not None:
+            import torch.distributed as dist
+
+            # every rank holds its own rows of the forward data: gather them in rank order
+            parts = [None] * dist.get_world_size(self.shard[2])
+            dist.all_gather_object(parts, data, group=self.shard[2])
+            data = np.concatenate(parts, axis=1)
         return model, data
 
     def launches(self):
@@ -109,6 +140,8 @@ class _KernelHolder:
         self.dsize, self.msize = int(mod.n_total), int(mod.M)
         self.mxs, self.mys, self.mzs = mod.mxs, mod.mys, mod.mzs
         self.Aw, self.Wm, self.WmInv, self.WmSquare = mod.Aw, mod.Wm, mod.WmInv, mod.WmSquare
+        # row-sharded (extension, `shard=(rank, world), group=`): this rank holds rows mod.rows of Aw
+        self._shard = (mod.rows, mod.n_total, mod.group) if mod.world > 1 else None
 
     @property
     def A(self):
@@ -206,9 +239,10 @@ class ConjugateGradient(_KernelHolder):
                              "used with a topography-carved model")
         mw0 = self.Wm @ np.asarray(initialModel, dtype=np.float64)
         mwapr = self.Wm @ np.asarray(apriorModel, dtype=np.float64)
-        h = _CgHandle(mod.Aw_pad, self.msize, self.dobs, mod.wm_dev, mod.wminv_dev, mod.wmsq_dev,
+        lo, hi = mod.rows
+        h = _CgHandle(mod.Aw_pad, self.msize, self.dobs[lo:hi], mod.wm_dev, mod.wminv_dev, mod.wmsq_dev,
                       _lib.CG_REGINV, _reg(regularization, self.mshape, beta), q, 0.001, boundary,
-                      ncols=1, mwapr=mwapr)
+                      ncols=1, mwapr=mwapr, shard=self._shard)
         try:
             iters, regul, dm, mm = h.run(mw0, maxk)
             model, data = h.result()
@@ -259,11 +293,11 @@ class BootStrap(_KernelHolder):
         r2 = mw * mw + self.beta ** 2
         return (2 * self.WmSquare @ (mw * self.beta ** 2)) / (r2 * r2)
 
-    def _solve(self, Aw_pad, dobs, initialModel, weights, ncols):
+    def _solve(self, Aw_pad, dobs, initialModel, weights, ncols, shard=None):
         mod = self._mod
         h = _CgHandle(Aw_pad, self.msize, dobs, mod.wm_dev, mod.wminv_dev, mod.wmsq_dev,
                       _lib.CG_BOOTSTRAP, _reg("MS", self.mshape, self.beta), 0.9, 0.1, self.boundary,
-                      ncols=ncols, weights=weights)
+                      ncols=ncols, weights=weights, shard=shard)
         try:
             mw0 = self.Wm @ np.asarray(initialModel, dtype=np.float64)
             iters, regul, dm, mm = h.run(mw0, self.maxk)
@@ -303,7 +337,10 @@ class BootStrap(_KernelHolder):
                 index = np.arange(0, self.dsize)
                 indexSample = np.random.choice(index, size=self.dsize, replace=True, p=None)
                 weights[c] = np.bincount(indexSample, minlength=self.dsize)
-            iters, regul, dm, mm, model = self._solve(mod.Aw_pad, self.dobs, initialModel, weights, ncols)
+            lo, hi = mod.rows  # row-sharded: this rank's rows of the data and of the multiplicities
+            iters, regul, dm, mm, model = self._solve(mod.Aw_pad, self.dobs[lo:hi], initialModel,
+                                                      np.ascontiguousarray(weights[:, lo:hi]), ncols,
+                                                      shard=self._shard)
             for c in range(ncols):
                 if int(iters[c]) < self.maxk:
                     # reginv.py:744-746: a replicate that stopped early returns short lists and the

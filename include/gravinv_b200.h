@@ -417,6 +417,17 @@ int gi_cg_create(const gi_cg_config *cfg, const double *G_dev, const double *dob
                  const double *wm_dev, const double *wminv_dev, const double *wmsq_dev,
                  const double *mwapr_host, const double *rowweight_host, void *stream, gi_cg **out);
 int gi_cg_destroy(gi_cg *h);
+/* Row-sharded CG (Aw partitioned by observation rows over GPUs): the handle is created
+ * over this rank's rows (cfg.N = local rows; dobs / rowweight = local rows) and told the global
+ * row count; at its exchange points it calls `hook` on its stream's behalf:
+ *   what 0: sum-reduce gt_dev[0 : Cp*ld]  (the adjoint output Aw^T (w r) of every column)
+ *   what 1: sum-reduce red_dev[0 : Cp]    (sum w q^2 or sum w r^2 per column)
+ * in place over every rank, ordered after the work already queued on the handle's stream.  Both
+ * buffers are caller-owned (Cp = ncols rounded up to 8, or 1).  Every other quantity is replicated
+ * and stays bitwise identical on all ranks (NCCL returns the same bits everywhere). */
+typedef int (*gi_cg_hook)(void *user, int32_t what);
+int gi_cg_set_shard(gi_cg *h, int64_t n_total, double *gt_dev, double *red_dev, gi_cg_hook hook,
+                    void *user);
 /* Run up to maxk iterations from mw0_host [M] = Wm @ initialModel (every column starts there).
  * Outputs (each optional): iters[ncols] = iterations executed (= entries of regul); regul
  * [ncols][maxk]; data_misfit / model_misfit [ncols][maxk] in the reference's list order (REGINV:

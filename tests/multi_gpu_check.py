@@ -66,8 +66,8 @@ def main():
     nacc = nrej = 0
     finals = {}
     for driver in ("device", "host"):
-        bt = batched.HMCBatch(model, nch, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
-                              "mandatory", 1000, dobs, 1.0, "MS", 0.001, 3, 1.0,
+        bt = batched.HMCBatch(model, nch, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
+                              "mandatory", 1000, dobs, 0.05, "MS", 0.001, 3, 0.05,
                               save_folder=os.path.join(tmp, "b%s%d_" % (driver, rank)), quiet=True,
                               driver=driver)
         assert (bt._sh is None) == (driver == "device")
@@ -78,8 +78,8 @@ def main():
             traces.append(tr)
         for c in range(nch):
             otr = []
-            onp.hmc_sample(om, 10 ** 6, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
-                           "mandatory", 1000, 1.0, "MS", 0.001, 3, 1.0, myrank=c, max_proposals=nprops,
+            onp.hmc_sample(om, 10 ** 6, 0, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
+                           "mandatory", 1000, 0.05, "MS", 0.001, 3, 0.05, myrank=c, max_proposals=nprops,
                            trace=otr)
             assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(t["L"], bool(t["accept"])) for t in otr]
             for k, t in enumerate(otr):
@@ -99,6 +99,7 @@ def main():
             assert all(torch.equal(xs[0], x) for x in xs)
             bt.close()
     assert np.allclose(finals["device"], finals["host"], rtol=1e-9, atol=0)
+    assert nacc > 0 and nrej >= 0  # the commit path ran (both drivers)
     # ---- streaming sampler over the row-sharded kernel (device driver), TV on the full grid ----
     bs = batched.HMCBatch(model, 6, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
                           "mandatory", 1000, dobs, 0.05, "TV", 0.001, 3, 0.05,
@@ -110,6 +111,27 @@ def main():
         assert [(L, bool(a)) for L, a in bs.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
         assert np.max(np.abs(bs.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"]))
     bs.close()
+    # ---- row-sharded regularised CG and bootstrap (gi_cg_set_shard) against the oracle ----
+    from gravinv3dhmc_b200.inversion import reginv
+
+    gr = np.load(os.path.join(ROOT, "tests", "golden", "reginv.npz"))
+    ob = gr["obs"]
+    cg = reginv.ConjugateGradient(gr["dobs"], (0, 800, 0, 600, 0, 400), (100, 100, 100),
+                                  (ob[:, 0].copy(), ob[:, 1].copy(), ob[:, 2].copy()), verbose=False,
+                                  shard=(rank, world), group=dist.group.WORLD)
+    rel = lambda a, b: np.max(np.abs(np.asarray(a) - b)) / np.max(np.abs(b))
+    for reg in ("MS", "TV"):
+        m, d, dm, mm, rf = cg.CG(gr["initial"], gr["aprior"], gr["boundary"], regularization=reg,
+                                 beta=float(gr["cg_%s_beta" % reg]), q=0.9, maxk=14)
+        assert rel(rf, gr["cg_%s_regul" % reg]) < 1e-9 and rel(dm, gr["cg_%s_data_misfit" % reg]) < 1e-9
+        assert rel(m, gr["cg_%s_model" % reg]) < 1e-9 and rel(d, gr["cg_%s_data" % reg]) < 1e-9
+    bsr = reginv.BootStrap((0, 800, 0, 600, 0, 400), (100, 100, 100),
+                           (ob[:, 0].copy(), ob[:, 1].copy(), ob[:, 2].copy()), gr["dobs"],
+                           tuple(gr["boundary"]), samples=5, beta=float(gr["bs_beta"]), maxk=9,
+                           verbose=False, shard=(rank, world), group=dist.group.WORLD)
+    mi, dmi, mmi, rfi = bsr.BSCG(gr["initial"])
+    assert rel(rfi, gr["bs_regul"]) < 1e-9 and rel(dmi, gr["bs_data_misfit"]) < 1e-9
+    assert rel(mi, gr["bs_models"]) < 1e-9
     dist.barrier()
     if rank == 0:
         print("multi_gpu_check ok: world=%d, %d accepted / %d rejected batch proposals match the oracle"
