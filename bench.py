@@ -441,7 +441,8 @@ def gpu_arm(args):
         # prepared on host threads while the GPU runs.  Measured over the steady-state window that
         # ends when the first chain has completed its quota of proposals (after that the batch
         # drains and chains run dry one by one).
-        nprop = max(4, int(round(args.steps / 12.5)) + 2)
+        nprop = max(5, int(round(args.steps / 12.5)) + 2)
+        bt.advance_cap = 4  # records (and the window's clock) come back every <= 4 batch steps
         bt.proposals = [[] for _ in range(nch)]
         window = {}
 
@@ -459,6 +460,9 @@ def gpu_arm(args):
                               props=sum(len(q) for q in bt.proposals) - window["p0"])
 
         bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
+        if window.get("steps", 0) <= 0:  # run too short for a steady-state window: use all of it
+            window.update(t=time.perf_counter() - t0, steps=bt.stream_steps,
+                          props=sum(len(q) for q in bt.proposals))
         api = ("HMCBatch.stream -> gi_hmcb_stream_feed_dev/advance (host RNG in the reference's order "
                "on background threads, draws staged host->device on a side stream, per-chain L in "
                "[5,20], chains restart inside the step they finish in; steady-state window of %d "

@@ -385,6 +385,7 @@ class HMCBatch:
         self._ahead = None
         self.output = "text"   # "text" (the reference's files) | "binary" | "none"  (inversion/sink.py)
         self.sink = None       # SampleSink(model, nslots=nchains): chain c -> slot c
+        self.advance_cap = None  # batch steps per gi_hmcb_stream_advance call (None: the whole runway)
         _lib.require_cuda()
         mw = self.initial_model
         if constraint == "logarithmic":     # hmc.py:271-273
@@ -683,7 +684,8 @@ class HMCBatch:
                 if run.value == 0:
                     break
                 _t1 = _time.perf_counter()
-                _lib.check(lib.gi_hmcb_stream_advance(self._h, run.value, recs, cap, C.byref(nrec),
+                nrun = run.value if self.advance_cap is None else min(run.value, int(self.advance_cap))
+                _lib.check(lib.gi_hmcb_stream_advance(self._h, nrun, recs, cap, C.byref(nrec),
                                                       C.byref(ndone), _lib.ptr(xh) if keep_x else None),
                            "gi_hmcb_stream_advance")
                 self.stream_steps += ndone.value
