@@ -10,8 +10,9 @@ misfit_and_grad, fd3d`), same exceptions.
 What differs by design:
   * `Aw` is a CUDA tensor ([N, M] view of a zero-padded [N, ld] buffer, `Aw_pad`) assembled and
     weighted in place on the device -- the unweighted `A` is never held separately (SURVEY H6);
-  * `njobs` is accepted and ignored; `field="magnetic"` is out of scope and raises the reference's
-    ValueError;
+  * `njobs` is accepted and ignored; `field="magnetic"` is supported for `coordinate="cartesian"`
+    (total-field anomaly kernel along `mangle`, potential.py:125-149); the reference's spherical
+    magnetic branch is an empty stub (potential.py:109-111) and raises its ValueError here;
   * `shard=(rank, world)` + `group=` (extension) keeps only this rank's observation rows
     (contiguous chunks like gravmag/prism.py:986-996) and sums the column norms with one
     all-reduce; everything else is replicated.
@@ -55,13 +56,16 @@ class GravMagModule:
         self.wavelet = wavelet
         self.coordinate = coordinate
 
-        if field != "gravity" or coordinate not in ("spherical", "cartesian"):
-            # potential.py:151 (the magnetic branches of the reference are outside this path)
+        magnetic = field == "magnetic" and coordinate == "cartesian"
+        if (field != "gravity" and not magnetic) or coordinate not in ("spherical", "cartesian"):
+            # potential.py:151 (the reference's spherical magnetic branch is an empty stub)
             raise ValueError("Please choose coordinate from(cartesian, spherical) and field "
                              "from(gravity, magnetic)!")
         self._say("Calculating {} field in {} coordinate.".format(field, coordinate))
         spherical = coordinate == "spherical"
-        if spherical:
+        if magnetic:  # potential.py:125-149: plain PrismMesh, total-field anomaly kernel
+            mesh = mesher.PrismMesh(mrange, mspacing, mratio)
+        elif spherical:
             mesh = (mesher.TesseroidMeshSegment(mrange, mspacing, mdivisionsection) if mseg
                     else mesher.TesseroidMesh(mrange, mspacing, mratio))
         else:
@@ -70,7 +74,12 @@ class GravMagModule:
         for key, value in kwargs.items():  # potential.py:94-98 / 116-120: any extra kwarg = topography
             self.topocarve = True
             self.mask = mesh.carvetopo(value[0], value[1], value[2])
-        mesh.addprop("density", np.zeros(mesh.size))
+        if magnetic:
+            from ..utils import ang2vec
+
+            mesh.addprop("magnetization", ang2vec(np.zeros(mesh.size), self.inc, self.dec))
+        else:
+            mesh.addprop("density", np.zeros(mesh.size))
         self.mesh = mesh
 
         n_total = len(self.lonobs)
@@ -87,6 +96,11 @@ class GravMagModule:
             table, _ = tesseroid._check_table(table)
             Apad, M = tesseroid.assemble(self.lonobs, self.latobs, self.heightobs, table,
                                          rows=self.rows, ncols=ncols)
+        elif magnetic:
+            from ..utils import dircos
+
+            Apad, M = prism.assemble_field("tf", self.lonobs, self.latobs, self.heightobs, table,
+                                           vec=dircos(self.inc, self.dec), rows=self.rows)
         else:
             # structured meshes share their corners: one evaluation per mesh node (bit-identical)
             out = prism.assemble_grid(self.lonobs, self.latobs, self.heightobs, mesh, rows=self.rows)

@@ -15,8 +15,8 @@ What differs by design:
   * `BootStrap.BSCG` batches up to 64 replicates as columns of the FP64 tensor-core contractions and
     expresses the row resampling (reginv.py:733-739) as row multiplicities, so Aw is never gathered
     into a second matrix and every pass over it serves all replicates of the batch;
-  * `njobs` is accepted and ignored; `field="magnetic"` raises the reference's ValueError
-    (reginv.py:97); `wavelet=` (compressed forward, arithmetic in PyWavelets) is supported by the
+  * `njobs` is accepted and ignored; `field="magnetic"` works for Cartesian grids (reginv.py:75-92),
+    the reference's spherical magnetic stub raises its ValueError (reginv.py:97); `wavelet=` (compressed forward, arithmetic in PyWavelets) is supported by the
     sampler path only and raises NotImplementedError here.
 """
 from __future__ import annotations
@@ -129,7 +129,8 @@ class _KernelHolder:
                                       "not part of this path; use the sampler or wavelet=False")
         verbose = kwargs.pop("verbose", True)
         mod = GravMagModule(dobs, mrange, mspacing, obsurface, mratio=mratio, weightfactor=0.5,
-                            coordinate=coordinate, njobs=njobs, field=field, wavelet=False,
+                            coordinate=coordinate, njobs=njobs, field=field,
+                            mangle=(getattr(self, "inc", 90), getattr(self, "dec", 0)), wavelet=False,
                             verbose=verbose, **kwargs)
         self._mod = mod
         if mod.topocarve:

@@ -224,7 +224,11 @@ def test_sensitivity_weighting_matches_reference(golden):
     assert Aw is model.Aw and (Wm @ np.ones(model.M)).shape == (model.M,)
     with pytest.raises(ValueError, match="coordinate"):
         potential.GravMagModule(g["small_dobs"], (0, 400, 0, 600, 0, 500), (100, 100, 100),
-                                (o[:, 0], o[:, 1], o[:, 2]), field="magnetic", verbose=False)
+                                (o[:, 0], o[:, 1], o[:, 2]), field="electric", verbose=False)
+    with pytest.raises(ValueError, match="coordinate"):  # the reference's spherical magnetic stub
+        potential.GravMagModule(g["small_dobs"], (0, 4, 0, 6, 0, -500), (-100, 1, 1),
+                                (o[:, 0], o[:, 1], o[:, 2]), coordinate="spherical", field="magnetic",
+                                verbose=False)
     assert np.array_equal(potential.GravMagModule.fd3d((2, 3, 4)).toarray(), g["fd3d_dense_2x3x4"])
 
 

@@ -103,3 +103,37 @@ def test_fields_vs_oracle_ragged(field):
         ores, oK = onp.prism_field(field, xp, yp, zp, tab, dens=dens, threads=4)
     assert nrm(K, oK) < 1e-10
     assert nrm(res, ores) < 1e-10
+
+
+def test_magnetic_module_and_chain_vs_reference_golden(golden, tmp_path):
+    """GravMagModule(coordinate="cartesian", field="magnetic") (potential.py:125-149): weighted tf
+    kernel, misfit_and_grad and a short chain against the unmodified reference"""
+    from gravinv3dhmc_b200.inversion import hmc, potential
+
+    g = golden["magnetic"]
+    o = g["obs"]
+    inc, dec = g["mangle"]
+    model = potential.GravMagModule(g["dobs"], (0, 400, 0, 600, 0, 500), (100, 100, 100),
+                                    (o[:, 0], o[:, 1], o[:, 2]), coordinate="cartesian", field="magnetic",
+                                    mangle=(inc, dec), verbose=False)
+    assert nrm(model.Aw.cpu().numpy(), g["Aw"]) < 1e-10
+    assert np.allclose(model.Wm.diagonal(), g["wm"], rtol=1e-10)
+    U, grad, dpre, Ud, Um = model.misfit_and_grad(g["mg_x"], g["mg_x0"], None, None, "mandatory", 1000, 0.7,
+                                                  regulization="MS", beta=0.001)
+    assert np.allclose([U, Ud, Um], g["mg_scalars"], rtol=1e-9)
+    assert nrm(grad, g["mg_grad"]) < 1e-9 and nrm(dpre, g["mg_dpre"]) < 1e-9
+    M = model.M
+    b = np.ones((M, 2))
+    b[:, 0], b[:, 1] = 0.0, 3.0
+    ch = hmc.HMCSample(model, 8, 0, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b, "mandatory",
+                       1000, g["dobs"], "Fixed", 0.8, 1.0, "Damping", 0.001, 21, 0.05, myrank=0,
+                       save_folder=str(tmp_path / "mag"), quiet=True)
+    log = g["chain_prop_log"]
+    assert [(L, int(a)) for L, a in ch.proposals] == [(int(L), int(a)) for L, a in log[:, :2]]
+    mis = np.loadtxt(tmp_path / "mag0" / "misfit.dat", ndmin=2)
+    mod = np.loadtxt(tmp_path / "mag0" / "model.dat", ndmin=2)
+    assert np.allclose(mis, g["chain_misfit"], rtol=0, atol=2e-8)
+    assert np.allclose(mod, g["chain_models"], rtol=0, atol=2e-8)
+    with pytest.raises(ValueError):
+        potential.GravMagModule(g["dobs"], (0, 10, 0, 10, 0, -1000), (-500, 5, 5), (o[:, 0], o[:, 1], o[:, 2]),
+                                coordinate="spherical", field="magnetic", verbose=False)

@@ -85,7 +85,14 @@ def test_cg_single_evaluations_and_errors(cg_small):
     with pytest.raises(ValueError):
         cg.CG(g["initial"], g["aprior"], g["boundary"], regularization="L1")
     with pytest.raises(ValueError):
-        reginv.ConjugateGradient(g["dobs"], MRANGE, MSPACING, obs_of(g), field="magnetic", verbose=False)
+        reginv.ConjugateGradient(g["dobs"], MRANGE, MSPACING, obs_of(g), field="electric", verbose=False)
+    # the Cartesian magnetic branch (reginv.py:75-92): same weighted tf kernel as GravMagModule
+    mag = reginv.ConjugateGradient(g["dobs"], MRANGE, MSPACING, obs_of(g), field="magnetic",
+                                   mangle=(55.0, -8.0), verbose=False)
+    xp, yp, zp = obs_of(g)
+    tab, _ = onp.OracleMesh(MRANGE, MSPACING).active_bounds()
+    _, K = onp.prism_field("tf", xp, yp, zp, tab, inc=55.0, dec=-8.0)
+    assert rel(mag.Aw.cpu().numpy(), onp.sensitivity_weighting(K)[0]) < 1e-10
 
 
 def test_cg_spherical_vs_reference_golden(golden):
