@@ -145,6 +145,7 @@ SIGNATURES = {
     "gi_hmcb_attach_stats": (C.c_int, [_P, _P, _P]),
     "gi_cg_create": (C.c_int, [C.POINTER(CgConfig), _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "gi_cg_destroy": (C.c_int, [_P]),
+    "gi_cg_set_wavelet": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _I64]),
     "gi_cg_set_shard": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "gi_cg_run": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
     "gi_cg_get_result": (C.c_int, [_P, _P, _P, _P]),

@@ -388,6 +388,12 @@ struct gi_cg {
     int *nactive_dev, *nactive_host;
     int32_t hist_maxk;
     int64_t launches;
+    // wavelet-compressed forward of the data terms (gi_cg_set_wavelet; 0 = off)
+    int wv_kind, wv_nz, wv_ny, wv_nx;
+    const int64_t *wv_indptr;
+    const int32_t *wv_indices;
+    const double *wv_data;
+    double *wv_coef;
     // row-sharded mode (gi_cg_set_shard): caller-owned reduction buffers + sum-reduce hook
     int64_t n_total;
     double *red, *gt_ext;  // [C] scalars; [C][ld] adjoint output
@@ -414,6 +420,7 @@ static void cg_free(gi_cg *h) {
     cudaFree(h->counter);
     cudaFree(h->nactive_dev);
     cudaFree(h->red_own);
+    cudaFree(h->wv_coef);
     if (h->nactive_host) cudaFreeHost(h->nactive_host);
     delete h;
 }
@@ -492,13 +499,53 @@ extern "C" int gi_cg_set_shard(gi_cg *h, int64_t n_total, double *gt_dev, double
     return GI_OK;
 }
 
+extern "C" int gi_cg_set_wavelet(gi_cg *h, int32_t kind, int32_t nz, int32_t ny, int32_t nx,
+                                 const int64_t *indptr, const int32_t *indices, const double *data,
+                                 int64_t ncoef) {
+    GI_REQUIRE(h, "gi_cg_set_wavelet: null handle");
+    GI_REQUIRE(kind == 0 || kind == 1 || kind == 3, "gi_cg_set_wavelet: kind must be 0, 1 or 3");
+    cudaFree(h->wv_coef);
+    h->wv_coef = nullptr;
+    h->wv_kind = 0;
+    if (kind == 0) return GI_OK;
+    GI_REQUIRE(h->cfg.ncols == 1 && !h->hook, "gi_cg_set_wavelet: single-column, unsharded handles only");
+    GI_REQUIRE(indptr && indices && data && ncoef > 0, "gi_cg_set_wavelet: null CSR arrays");
+    int64_t want = 0;
+    if (kind == 1) {
+        int rc = gi_dwt_db4_l2_1d(nullptr, h->cfg.M, nullptr, &want, nullptr);
+        if (rc) return rc;
+    } else {
+        GI_REQUIRE((int64_t)nz * ny * nx == h->cfg.M,
+                   "gi_cg_set_wavelet: the 3-D wavelet needs the full (nz, ny, nx) grid");
+        int32_t shp[3];
+        int rc = gi_dwt_db4_l2_3d(nullptr, nz, ny, nx, nullptr, shp, nullptr);
+        if (rc) return rc;
+        want = (int64_t)shp[0] * shp[1] * shp[2];
+    }
+    GI_REQUIRE(want == ncoef, "gi_cg_set_wavelet: CSR column count does not match the transform");
+    GI_CUDA(cudaMalloc(&h->wv_coef, sizeof(double) * ncoef));
+    h->wv_kind = kind; h->wv_nz = nz; h->wv_ny = ny; h->wv_nx = nx;
+    h->wv_indptr = indptr; h->wv_indices = indices; h->wv_data = data;
+    return GI_OK;
+}
+
 extern "C" int gi_cg_destroy(gi_cg *h) {
     cg_free(h);
     return GI_OK;
 }
 
-// D[c] = Aw X[c] for every column
-static int cg_forward(gi_cg *h, const double *X) {
+// D[c] = Aw X[c] for every column.  `data_term`: this forward feeds data(mw) / data_gfun(mw)
+// (reginv.py:248-269), which go through the wavelet-compressed kernel when one is set -- the step
+// length's Aw @ Iw (reginv.py:425) and the final A @ model_inv (:490) stay dense, as in the reference.
+static int cg_forward(gi_cg *h, const double *X, bool data_term = false) {
+    if (data_term && h->wv_kind) {
+        int rc = h->wv_kind == 1
+                     ? gi_dwt_db4_l2_1d(X, h->cfg.M, h->wv_coef, nullptr, h->s)
+                     : gi_dwt_db4_l2_3d(X, h->wv_nz, h->wv_ny, h->wv_nx, h->wv_coef, nullptr, h->s);
+        if (rc) return rc;
+        h->launches += (h->wv_kind == 1 ? 2 : 7);
+        return gi_csr_spmv(h->wv_indptr, h->wv_indices, h->wv_data, h->cfg.N, h->wv_coef, h->D, h->s);
+    }
     h->launches += 2;
     if (h->cfg.ncols == 1) return gi_gemv_fwd(h->plan, h->G, X, h->D, h->s);
     return gi_gemm_fwd(h->plan, h->G, X, h->D, h->s);
@@ -558,7 +605,7 @@ extern "C" int gi_cg_run(gi_cg *h, const double *mw0_host, int32_t maxk, int32_t
     int rc;
     // start point: R(mw0), dR(mw0), d = Aw mw0, r, data(mw0)
     if ((rc = cg_model(h))) return rc;
-    if ((rc = cg_forward(h, h->mw))) return rc;
+    if ((rc = cg_forward(h, h->mw, true))) return rc;
     if ((rc = cg_resid(h, -1, maxk))) return rc;
     for (int k = 0; k < maxk; ++k) {
         cg_alpha_kernel<<<1, 64, 0, s>>>(h->S, C, k, h->cfg.q, h->hist, maxk);
@@ -577,7 +624,7 @@ extern "C" int gi_cg_run(gi_cg *h, const double *mw0_host, int32_t maxk, int32_t
         GI_LAUNCH_CHECK();
         h->launches += 6;
         if ((rc = cg_model(h))) return rc;
-        if ((rc = cg_forward(h, h->mw))) return rc;
+        if ((rc = cg_forward(h, h->mw, true))) return rc;
         if ((rc = cg_resid(h, k, maxk))) return rc;
         // the reference's early stop (reginv.py:486-488 / 693-696): one 4-byte read per iteration
         GI_CUDA(cudaMemcpyAsync(h->nactive_host, h->nactive_dev, sizeof(int), cudaMemcpyDeviceToHost, s));

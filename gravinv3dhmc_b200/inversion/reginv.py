@@ -16,8 +16,12 @@ What differs by design:
     expresses the row resampling (reginv.py:733-739) as row multiplicities, so Aw is never gathered
     into a second matrix and every pass over it serves all replicates of the batch;
   * `njobs` is accepted and ignored; `field="magnetic"` works for Cartesian grids (reginv.py:75-92),
-    the reference's spherical magnetic stub raises its ValueError (reginv.py:97); `wavelet=` (compressed forward, arithmetic in PyWavelets) is supported by the
-    sampler path only and raises NotImplementedError here.
+    the reference's spherical magnetic stub raises its ValueError (reginv.py:97);
+  * `wavelet='1D'/'3D'` (reginv.py:107-117, 250-264): the data terms of `ConjugateGradient` go through
+    the compressed kernel on the device (`gi_cg_set_wavelet`), single GPU; the arithmetic is
+    PyWavelets' (restated, parity unpinned -- DESIGN.md section 5).  `BootStrap` keeps the dense
+    kernel: the reference's compressed bootstrap forward ignores the resampling (reginv.py:590-593
+    applies the full-row `Awcp` to resampled data), which is not reproduced.
 """
 from __future__ import annotations
 
@@ -81,6 +85,13 @@ class _CgHandle:
             _lib.check(self.L.gi_cg_set_shard(self.h, int(n_total), _lib.ptr(self._gt), _lib.ptr(self._red),
                                               self._hook, None), "gi_cg_set_shard")
 
+    def set_wavelet(self, kind, mshape, Awcp):
+        nz, ny, nx = (int(v) for v in mshape)
+        self._keep += (Awcp,)
+        _lib.check(self.L.gi_cg_set_wavelet(self.h, 1 if kind == "1D" else 3, nz, ny, nx,
+                                            _lib.ptr(Awcp.indptr), _lib.ptr(Awcp.indices),
+                                            _lib.ptr(Awcp.data), Awcp.shape[1]), "gi_cg_set_wavelet")
+
     def run(self, mw0, maxk):
         mw0 = np.ascontiguousarray(mw0, dtype=np.float64)
         iters = np.zeros(self.ncols, dtype=np.int32)
@@ -124,14 +135,15 @@ class _KernelHolder:
 
     def _build(self, dobs, mrange, mspacing, obsurface, mratio, njobs, coordinate, field, wavelet,
                kwargs):
-        if wavelet:
-            raise NotImplementedError("reginv with wavelet='1D'/'3D' (PyWavelets arithmetic) is "
-                                      "not part of this path; use the sampler or wavelet=False")
         verbose = kwargs.pop("verbose", True)
         mod = GravMagModule(dobs, mrange, mspacing, obsurface, mratio=mratio, weightfactor=0.5,
                             coordinate=coordinate, njobs=njobs, field=field,
-                            mangle=(getattr(self, "inc", 90), getattr(self, "dec", 0)), wavelet=False,
+                            mangle=(getattr(self, "inc", 90), getattr(self, "dec", 0)), wavelet=wavelet,
                             verbose=verbose, **kwargs)
+        if wavelet in ("1D", "3D"):  # reginv.py:107-117: the compressed kernel of the data terms
+            if mod.world > 1:
+                raise NotImplementedError("the wavelet-compressed forward is a single-GPU path")
+            self.Awcp = mod.Awcp
         self._mod = mod
         if mod.topocarve:
             self.topocarve = True
@@ -169,7 +181,10 @@ class _KernelHolder:
     def _resid(self, mw, pad, dobs=None):
         torch = _lib.require_cuda()
         mw = torch.as_tensor(np.asarray(mw, dtype=np.float64), device=pad.device)
-        d = matvec_padded(pad, self.msize, mw, torch)
+        if getattr(self, "wavelet", False) in ("1D", "3D") and pad is self._mod.Aw_pad:
+            d = self._mod._forward(mw)  # reginv.py:250-253: the compressed kernel
+        else:
+            d = matvec_padded(pad, self.msize, mw, torch)
         return d - torch.as_tensor(np.asarray(self.dobs if dobs is None else dobs, dtype=np.float64),
                                    device=d.device)
 
@@ -244,6 +259,8 @@ class ConjugateGradient(_KernelHolder):
         h = _CgHandle(mod.Aw_pad, self.msize, self.dobs[lo:hi], mod.wm_dev, mod.wminv_dev, mod.wmsq_dev,
                       _lib.CG_REGINV, _reg(regularization, self.mshape, beta), q, 0.001, boundary,
                       ncols=1, mwapr=mwapr, shard=self._shard)
+        if self.wavelet in ("1D", "3D"):
+            h.set_wavelet(self.wavelet, self.mshape, self.Awcp)
         try:
             iters, regul, dm, mm = h.run(mw0, maxk)
             model, data = h.result()
@@ -274,7 +291,7 @@ class BootStrap(_KernelHolder):
         self.maxk, self.beta, self.wavelet = maxk, beta, wavelet
         self.batch = int(kwargs.pop("batch", 64))  # extension: replicates per pass over Aw (<= 64)
         self._build(self.dobs, mrange, mspacing, obsurface, mratio, njobs, "cartesian", "gravity",
-                    wavelet, kwargs)
+                    False, kwargs)
         self.last_launches = 0
 
     # reginv.py:588-629

@@ -425,6 +425,12 @@ int gi_cg_destroy(gi_cg *h);
  * in place over every rank, ordered after the work already queued on the handle's stream.  Both
  * buffers are caller-owned (Cp = ncols rounded up to 8, or 1).  Every other quantity is replicated
  * and stays bitwise identical on all ranks (NCCL returns the same bits everywhere). */
+/* Wavelet-compressed data terms (reginv.py:250-253, 261-264): d = Awcp @ DWT(mw) replaces Aw @ mw in
+ * data(mw) / data_gfun(mw); Aw @ Iw of the step length and Aw^T stay dense, as in the reference.
+ * Same arguments as gi_hmc_set_wavelet; single-column, unsharded handles. */
+int gi_cg_set_wavelet(gi_cg *h, int32_t kind, int32_t nz, int32_t ny, int32_t nx,
+                      const int64_t *indptr_dev, const int32_t *indices_dev, const double *data_dev,
+                      int64_t ncoef);
 typedef int (*gi_cg_hook)(void *user, int32_t what);
 int gi_cg_set_shard(gi_cg *h, int64_t n_total, double *gt_dev, double *red_dev, gi_cg_hook hook,
                     void *user);

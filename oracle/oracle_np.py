@@ -904,8 +904,9 @@ class OracleCG:
     """``ConjugateGradient`` of inversion/reginv.py:22-491 from an explicit weighted kernel.
     ``A`` is the unweighted kernel (reginv.py:489 forwards the result through it)."""
 
-    def __init__(self, A, dobs, mshape):
+    def __init__(self, A, dobs, mshape, wavelet=False):
         # reginv.py:120-149 newkernel (the fixed np.sqrt instead of weightfactor)
+        self.wavelet = wavelet
         self.A = np.asarray(A, dtype=np.float64)
         self.Aw, self.wm, self.wminv, self.wmsq = sensitivity_weighting(self.A, 0.5)
         self.wm = np.sqrt(self.wm * self.wm)  # reginv.py:129 (sqrt of the sum of squares)
@@ -913,17 +914,28 @@ class OracleCG:
         self.mshape = tuple(mshape)
         self.dsize, self.msize = self.A.shape
         self._R = None
+        if wavelet == "1D":  # reginv.py:107-117 (PyWavelets restated: parity unpinned)
+            self.Awcp = kernelcompressor_1d(self.Aw)
+        elif wavelet == "3D":
+            self.Awcp = kernelcompressor_3d(self.Aw, self.mshape)
 
     def R3d(self):
         if self._R is None:
             self._R = fd3d(self.mshape)  # reginv.py:151-246 is the same builder as potential.py
         return self._R
 
+    def _dpre(self, mw):  # reginv.py:250-255
+        if self.wavelet == "1D":
+            return modelcompressor_1d(mw, self.Awcp)
+        if self.wavelet == "3D":
+            return modelcompressor_3d(mw, self.Awcp, self.mshape)
+        return np.dot(self.Aw, mw)
+
     def data(self, mw):  # reginv.py:248-257
-        return np.linalg.norm(np.dot(self.Aw, mw) - self.dobs) ** 2
+        return np.linalg.norm(self._dpre(mw) - self.dobs) ** 2
 
     def data_gfun(self, mw):  # reginv.py:259-269
-        return 2 * np.dot(self.Aw.T, (np.dot(self.Aw, mw) - self.dobs))
+        return 2 * np.dot(self.Aw.T, (self._dpre(mw) - self.dobs))
 
     def model(self, reg, mw, mwapr, beta):
         if reg == "MS":  # reginv.py:271-281

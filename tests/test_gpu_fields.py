@@ -137,3 +137,32 @@ def test_magnetic_module_and_chain_vs_reference_golden(golden, tmp_path):
     with pytest.raises(ValueError):
         potential.GravMagModule(g["dobs"], (0, 10, 0, 10, 0, -1000), (-500, 5, 5), (o[:, 0], o[:, 1], o[:, 2]),
                                 coordinate="spherical", field="magnetic", verbose=False)
+
+
+def test_field_edge_cases():
+    """empty and degenerate inputs of the field builders (prism.py:136-137 skips cells without the
+    property; zero observations / zero cells must not launch anything)"""
+    from gravinv3dhmc_b200.gravmag import tesseroid
+
+    mesh = mesher.PrismMesh(MRANGE, MSPACING)
+    mesh.addprop("density", np.ones(mesh.size))
+    e = np.zeros(0)
+    res, K = prism.gyz(e, e, e, mesh)
+    assert res.shape == (0,) and K.shape == (0, mesh.size)
+    res, K = prism.tf(e, e, e, mesh, 10.0, 20.0, pmag=1.0)
+    assert res.shape == (0,) and K.shape == (0, mesh.size)
+    one = np.array([123.0]), np.array([77.0]), np.array([-3.0])
+    res, K = prism.potential(*one, [None, None])          # a model of masked cells only
+    assert K.shape == (1, 0) and res[0] == 0.0
+    tm = mesher.TesseroidMesh((-2, 2, -2, 2, 0, -20000), (-10000, 2, 2))
+    res, K = tesseroid.gxz(e, e, e, tm, dens=1.0)
+    assert res.shape == (0,) and K.shape == (0, tm.size)
+    # a single (observation, cell) pair straight above the cell centre: gxz = gyz = 0 by symmetry
+    cell = mesher.PrismMesh((0, 100, 0, 100, 0, 100), (100, 100, 100))
+    cell.addprop("density", np.ones(1))
+    c = np.array([50.0]), np.array([50.0]), np.array([-40.0])
+    for f in ("gxz", "gyz", "gxy", "gx", "gy"):
+        assert abs(getattr(prism, f)(*c, cell)[0][0]) < 1e-9 * abs(prism.gzz(*c, cell)[0][0])
+    # Laplace: gxx + gyy + gzz = 0 outside the body
+    lap = sum(getattr(prism, f)(*c, cell)[0][0] for f in ("gxx", "gyy", "gzz"))
+    assert abs(lap) < 1e-9 * abs(prism.gzz(*c, cell)[0][0])
