@@ -1,0 +1,340 @@
+// fused.cu -- ONE pass over the weighted kernel per gradient evaluation of a single chain:
+//     d = Aw x          (inversion/potential.py:698  dpre = np.dot(self.Aw, mw))
+//     g = Aw^T r        (potential.py:708            2 * np.dot(self.Aw.T, r), factor 2 applied later)
+//     r = (d + fix - mean(d + fix)) - dobs_c         (potential.py:699-706)
+// The two GEMV passes of gemv_fwd_kernel / gemv_adj_kernel each stream Aw from HBM (2 x 8 N M bytes
+// per evaluation).  r depends on ALL of d through the mean, but linearly:  Aw^T r = Aw^T e - mean * s
+// with e = d + fix - dobs_c (row-local) and s = Aw^T 1 (precomputed once), so row i's contribution to
+// the adjoint can be added as soon as d_i is complete -- while the row is still ON CHIP.
+//
+// Persistent kernel, one CTA per SM (cooperative launch => co-resident).  CTA b owns the column strip
+// [b W, (b+1) W) for every row: its slice of x and of the adjoint accumulator live in registers.
+// Rows stream through a 4-slot shared-memory ring filled by 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx), ~2 rows (2 x 56 KB at M = 2^20) in flight per SM.
+//   phase 1 (row i)     : partial dot of the strip with x, published as a 16-byte {value, tag} pair
+//                         in ONE vector store (no fence, no flag);
+//   phase 2 (row i - 2) : every CTA polls the 148 pairs of that row (the poll is issued an iteration
+//                         early, its L2 round trip hides under the arithmetic), sums them in a fixed
+//                         order (identical bits on every CTA), forms e and adds
+//                         e * row-strip -- read from SHARED memory, not from HBM -- to its accumulator;
+//                         the slot is then refilled with row i + 2.
+// No atomics (a same-address counter would serialise 148 L2 atomics per row), no grid-wide barrier:
+// a CTA only ever waits for rows published two iterations earlier.  DRAM traffic per evaluation is
+// 8 N M bytes instead of 16 N M; the result is deterministic (fixed strip ownership and summation
+// order).  Rounding differs from the two-pass form at the 1e-16 * |mean s| / |Aw^T r| level (~1e-14),
+// far inside the 1e-9 parity bar of the trajectories.
+#include <algorithm>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gi {
+namespace {
+
+constexpr int kFT = 256;    // threads per CTA
+constexpr int kFS = 4;      // ring slots
+constexpr int kFLag = 2;    // rows between publishing a partial and consuming the complete row
+constexpr int kFU = 7;      // double4 chunks per thread at most -> strip width <= 7168 columns
+constexpr int kFCtas = 1;   // CTAs per SM (2 with half strips was slower: the hand-off costs ~ P^2)
+constexpr int kFQ = 1;      // partials polled per thread -> up to 256 CTAs
+constexpr unsigned long long kSpinLimit = 1ull << 26;
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void lds4(unsigned a, double &x0, double &x1, double &x2, double &x3) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x2), "=d"(x3) : "r"(a + 16));
+}
+
+struct FusedArgs {
+    const double *G;
+    int64_t ld, nrows, W;
+    const double *x, *dobs_c, *fix, *s;
+    double inv_n;
+    unsigned long long *part;     // [nrows][P] {value bits, tag = epoch_base + row + 1}
+    unsigned long long epoch_base;
+    double *mean_io;  // [2] mean of the previous / this evaluation (ping-pong by launch parity)
+    int mean_slot;
+    long long *dbg;   // optional [8]: clock64 sums per phase (CTA 0, thread 0)
+    double *d_out, *g_out;
+};
+
+__global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int P = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t W = a.W, c0 = (int64_t)b * W;
+    const int64_t rem = a.ld - c0;
+    const int64_t Wb = rem <= 0 ? 0 : (rem < W ? rem : W);
+    const unsigned bytes = (unsigned)(Wb * 8);
+    double *ring = reinterpret_cast<double *>(smem);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + (size_t)kFS * W * 8);
+    double *scratch = reinterpret_cast<double *>(full + kFS);
+    const unsigned ring_a = smem_addr(ring), full_a = smem_addr(full);
+
+    // this thread's slice of x and of the adjoint accumulator: chunk k = tid + 256 u covers strip
+    // columns 4k .. 4k+3
+    double xv[kFU][4], ga[kFU][4];
+#pragma unroll
+    for (int u = 0; u < kFU; ++u) {
+        const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
+        if (k4 < Wb) ldg4(a.x + c0 + k4, xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
+        else xv[u][0] = xv[u][1] = xv[u][2] = xv[u][3] = 0.0;
+        ga[u][0] = ga[u][1] = ga[u][2] = ga[u][3] = 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kFS; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_a + 8 * s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t row) {  // thread 0: fill slot row % kFS with the strip of `row`
+        const int slot = (int)(row % kFS);
+        const unsigned bar = full_a + 8 * slot;
+        if (bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    ring_a + (unsigned)(slot * W * 8)),
+                "l"(a.G + row * a.ld + c0), "r"(bytes), "r"(bar)
+                : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+    };
+    if (tid == 0)
+        for (int64_t r = 0; r < kFS && r < a.nrows; ++r) issue(r);
+
+    // Partials travel as 16-byte {value, tag} pairs written with ONE vector store and polled with ONE
+    // vector load (no fence, no separate flag: aligned 16-byte accesses are single transactions, the
+    // protocol NCCL's LL128 also builds on); tag = epoch_base + row + 1 never repeats across launches.
+    // The poll for row j is issued one iteration early and only CHECKED when the row is consumed, so
+    // its L2 round trip hides under the arithmetic of the rows in between.
+    auto poll = [&](int64_t row, unsigned long long &v, unsigned long long &tag) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];"
+                     : "=l"(v), "=l"(tag)
+                     : "l"(a.part + 2 * (row * P + tid))
+                     : "memory");
+    };
+    // Iteration i: forward dot of row i (published), then the adjoint update with row j = i - 2.
+    const double m0 = a.mean_io[a.mean_slot];  // last evaluation's mean: e is formed around it, so
+    double sd = 0.0;                           // the correction mean' * s below stays small
+    unsigned long long pv = 0, ptag = 0;       // prefetched partial of the row consumed NEXT iteration
+    for (int64_t i = 0; i < a.nrows + kFLag; ++i) {
+        const int64_t j = i - kFLag;
+        unsigned long long cv = pv, ctag = ptag;  // partial of row j, polled during iteration i - 1
+        if (tid < P && j + 1 >= 0 && j + 1 < a.nrows) poll(j + 1, pv, ptag);
+        double acc = 0.0;
+        if (i < a.nrows) {
+            // ---- phase 1: partial dot product of row i with this CTA's slice of x ------------
+            const int slot = (int)(i % kFS);
+            const unsigned bar = full_a + 8 * slot, parity = (unsigned)((i / kFS) & 1);
+            unsigned done = 0;
+            while (!done)
+                asm volatile(
+                    "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(done)
+                    : "r"(bar), "r"(parity)
+                    : "memory");
+            const unsigned row_a = ring_a + (unsigned)(slot * W * 8);
+#pragma unroll
+            for (int u = 0; u < kFU; ++u) {
+                const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
+                if (k4 < Wb) {
+                    double g0, g1, g2, g3;
+                    lds4(row_a + (unsigned)(k4 * 8), g0, g1, g2, g3);
+                    acc = fma(g0, xv[u][0], acc);
+                    acc = fma(g1, xv[u][1], acc);
+                    acc = fma(g2, xv[u][2], acc);
+                    acc = fma(g3, xv[u][3], acc);
+                }
+            }
+        }
+        double v = 0.0;
+        if (j >= 0 && tid < P) {
+            // the complete row j: this thread's share is CTA `tid`'s partial
+            const unsigned long long target = a.epoch_base + (unsigned long long)j + 1ull;
+            unsigned long long spins = 0;
+            while (ctag != target) {
+                poll(j, cv, ctag);
+                if (++spins > kSpinLimit) __trap();
+            }
+            v = __longlong_as_double((long long)cv);
+        }
+        // one block-wide reduction for both: acc -> this CTA's partial of row i (thread 0 publishes),
+        // v -> d_j in a fixed order (identical bits on every CTA)
+        acc = warp_sum(acc);
+        v = warp_sum(v);
+        if (lane == 0) { scratch[warp] = acc; scratch[8 + warp] = v; }  // (free since the last barrier)
+        __syncthreads();
+        if (tid == 0 && i < a.nrows) {
+            double t = 0.0;
+            for (int w = 0; w < kFT / 32; ++w) t += scratch[w];
+            const unsigned long long tag = a.epoch_base + (unsigned long long)i + 1ull;
+            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(a.part + 2 * (i * P + b)),
+                         "l"((unsigned long long)__double_as_longlong(t)), "l"(tag)
+                         : "memory");
+        }
+        if (j >= 0) {
+            // ---- phase 2: add e_j * (row j strip, still in shared memory) to the accumulator ---
+            double dj = 0.0;
+            for (int w = 0; w < kFT / 32; ++w) dj += scratch[8 + w];
+            const double dinv = (a.fix ? dj + __ldg(a.fix + j) : dj) - m0;
+            const double ej = dinv - __ldg(a.dobs_c + j);
+            sd += dinv;
+            const unsigned row_a = ring_a + (unsigned)((int)(j % kFS) * W * 8);
+#pragma unroll
+            for (int u = 0; u < kFU; ++u) {
+                const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
+                if (k4 < Wb) {
+                    double g0, g1, g2, g3;
+                    lds4(row_a + (unsigned)(k4 * 8), g0, g1, g2, g3);
+                    ga[u][0] = fma(g0, ej, ga[u][0]);
+                    ga[u][1] = fma(g1, ej, ga[u][1]);
+                    ga[u][2] = fma(g2, ej, ga[u][2]);
+                    ga[u][3] = fma(g3, ej, ga[u][3]);
+                }
+            }
+            if (tid == 0 && b == (int)(j % P)) a.d_out[j] = dj;
+            __syncthreads();  // every thread is done with slot j % kFS (and with scratch)
+            if (tid == 0 && j + kFS < a.nrows) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(j + kFS);
+            }
+        } else {
+            __syncthreads();  // scratch is reused next iteration
+        }
+    }
+    // g = Aw^T e - mean' * s   (r = e - mean', mean' = mean - m0)
+    const double mean = sd * a.inv_n;
+    if (b == 0 && tid == 0) a.mean_io[a.mean_slot ^ 1] = m0 + mean;
+#pragma unroll
+    for (int u = 0; u < kFU; ++u) {
+        const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
+        if (k4 < Wb) {
+            double s0, s1, s2, s3;
+            ldg4(a.s + c0 + k4, s0, s1, s2, s3);
+            stg4(a.g_out + c0 + k4, ga[u][0] - mean * s0, ga[u][1] - mean * s1, ga[u][2] - mean * s2,
+                 ga[u][3] - mean * s3);
+        }
+    }
+}
+
+__global__ void fill_kernel(double *p, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace
+}  // namespace gi
+
+using namespace gi;
+
+struct gi_fused {
+    int64_t nrows, M, ld, W;
+    int P;
+    size_t smem;
+    const double *G;
+    double *s, *mean_io;
+    long long *dbg;  // GI_FUSED_PROFILE=1: per-phase clock sums of CTA 0 (diagnostics)
+    unsigned long long *part, epoch, nlaunch;
+    int64_t launches;
+};
+
+extern "C" int gi_fused_destroy(gi_fused *f) {
+    if (!f) return GI_OK;
+    cudaFree(f->s);
+    cudaFree(f->part);
+    cudaFree(f->mean_io);
+    cudaFree(f->dbg);
+    delete f;
+    return GI_OK;
+}
+
+extern "C" int gi_fused_create(int64_t nrows, int64_t M, int64_t ld, const double *G_dev, void *stream,
+                               gi_fused **out) {
+    GI_REQUIRE(out && G_dev && nrows > 0 && M > 0 && ld >= M && ld % 4 == 0, "gi_fused_create: bad argument");
+    int dev = 0, coop = 0, max_smem = 0;
+    GI_CUDA(cudaGetDevice(&dev));
+    GI_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GI_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int P = kFCtas * sm_count();
+    const int64_t W = ceil_div(ceil_div(ld, (int64_t)P), 4) * 4;
+    const size_t smem = (size_t)kFS * W * 8 + kFS * 8 + 32 * 8;
+    GI_REQUIRE(coop, "gi_fused_create: the device does not support cooperative launches");
+    GI_REQUIRE(P <= kFT * kFQ, "gi_fused_create: more CTAs than partial slots per thread");
+    GI_REQUIRE(W <= 4LL * kFT * kFU && W % 2 == 0 && smem <= (size_t)max_smem,
+               "gi_fused_create: the column strip of one SM (%lld columns) does not fit its shared memory",
+               (long long)W);
+    GI_CUDA(cudaFuncSetAttribute(fused_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    GI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_pass_kernel, kFT, smem));
+    GI_REQUIRE(per_sm >= kFCtas, "gi_fused_create: the CTAs of one SM do not fit it together");
+    gi_fused *f = new gi_fused();
+    memset(f, 0, sizeof(*f));
+    f->nrows = nrows; f->M = M; f->ld = ld; f->W = W; f->P = P; f->smem = smem; f->G = G_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc(&f->s, sizeof(double) * ld);
+    if (e == cudaSuccess) e = cudaMalloc(&f->part, 16 * (size_t)nrows * P);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->part, 0, 16 * (size_t)nrows * P, st);
+    if (e == cudaSuccess) e = cudaMalloc(&f->mean_io, 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->mean_io, 0, 2 * sizeof(double), st);
+    if (e == cudaSuccess && getenv("GI_FUSED_PROFILE")) e = cudaMalloc(&f->dbg, 8 * sizeof(long long));
+    if (e != cudaSuccess) {
+        gi_fused_destroy(f);
+        return cuda_fail(e, "gi_fused_create", __FILE__, __LINE__);
+    }
+    // s = Aw^T 1 through the deterministic adjoint pass
+    gi_plan *plan = nullptr;
+    double *ones = nullptr;
+    int rc = gi_plan_create(nrows, M, ld, 1, &plan);
+    if (!rc) {
+        e = cudaMalloc(&ones, sizeof(double) * nrows);
+        if (e != cudaSuccess) rc = cuda_fail(e, "gi_fused_create", __FILE__, __LINE__);
+    }
+    if (!rc) {
+        fill_kernel<<<(unsigned)ceil_div(nrows, 256), 256, 0, st>>>(ones, nrows, 1.0);
+        rc = gi_gemv_adj(plan, G_dev, ones, f->s, st);
+    }
+    if (!rc) {
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "gi_fused_create", __FILE__, __LINE__);
+    }
+    cudaFree(ones);
+    gi_plan_destroy(plan);
+    if (rc) {
+        gi_fused_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return GI_OK;
+}
+
+// diagnostics: the per-phase clock sums of the last pass (zeros unless GI_FUSED_PROFILE is set)
+extern "C" int gi_fused_profile(gi_fused *f, int64_t *clocks8_host) {
+    GI_REQUIRE(f && clocks8_host, "gi_fused_profile: null pointer");
+    memset(clocks8_host, 0, 8 * sizeof(int64_t));
+    if (f->dbg) GI_CUDA(cudaMemcpy(clocks8_host, f->dbg, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return GI_OK;
+}
+
+extern "C" int gi_fused_pass(gi_fused *f, const double *x_dev, const double *dobs_c_dev, const double *fix_dev,
+                             double *d_dev, double *g_dev, void *stream) {
+    GI_REQUIRE(f && x_dev && dobs_c_dev && d_dev && g_dev, "gi_fused_pass: null pointer");
+    FusedArgs a;
+    a.G = f->G; a.ld = f->ld; a.nrows = f->nrows; a.W = f->W;
+    a.x = x_dev; a.dobs_c = dobs_c_dev; a.fix = fix_dev; a.s = f->s;
+    a.inv_n = 1.0 / (double)f->nrows;
+    a.part = f->part; a.epoch_base = f->epoch;
+    a.mean_io = f->mean_io; a.mean_slot = (int)(f->nlaunch & 1ull);
+    a.dbg = f->dbg;
+    f->nlaunch += 1;
+    a.d_out = d_dev; a.g_out = g_dev;
+    f->epoch += (unsigned long long)f->nrows + 1ull;
+    void *args[] = {&a};
+    GI_CUDA(cudaLaunchCooperativeKernel((void *)fused_pass_kernel, dim3((unsigned)f->P), dim3(kFT), args, f->smem,
+                                        (cudaStream_t)stream));
+    f->launches += 1;
+    return GI_OK;
+}

@@ -18,6 +18,7 @@
 // No floating-point atomics anywhere: results are bitwise reproducible run to run.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -444,6 +445,10 @@ struct gi_hmc {
     const double *wv_data;
     int64_t wv_ncoef;
     double *wv_coef;
+    // single-pass gradient evaluation (fused.cu): -1 not tried yet, 0 unavailable, 1 in use
+    int fused_state;
+    gi_fused *fused;
+    double *gfused;
     // on-device sample sink (gi_hmc_attach_stats)
     gi_stats *stats;
     int32_t stats_slot;
@@ -460,9 +465,34 @@ static void hmc_free(gi_hmc *h) {
     }
     cudaFree(h->st);
     cudaFree(h->wv_coef);
+    cudaFree(h->gfused);
+    gi_fused_destroy(h->fused);
     if (h->st_host) cudaFreeHost(h->st_host);
     gi_plan_destroy(h->plan);
     delete h;
+}
+
+// The fused single-pass evaluation pays one cross-SM hand-off per observation row, so it only wins
+// when a row strip is worth streaming: kernels of >= 1 GB by default (GI_FUSED_GEMV=1 forces it on
+// for any shape that fits, =0 switches it off).  Falls back silently to the two-pass kernels.
+static bool fused_ready(gi_hmc *h) {
+    if (h->fused_state >= 0) return h->fused_state == 1;
+    h->fused_state = 0;
+    const char *env = getenv("GI_FUSED_GEMV");
+    if (env && env[0] == '0') return false;
+    const bool force = env && env[0] == '1';
+    if (!force && (double)h->cfg.N * (double)h->cfg.ld * 8.0 < 1e9) return false;
+    if (gi_fused_create(h->cfg.N, h->cfg.M, h->cfg.ld, h->G, h->stream, &h->fused) != GI_OK) {
+        h->fused = nullptr;
+        return false;
+    }
+    if (cudaMalloc(&h->gfused, sizeof(double) * h->cfg.ld) != cudaSuccess) {
+        gi_fused_destroy(h->fused);
+        h->fused = nullptr;
+        return false;
+    }
+    h->fused_state = 1;
+    return true;
 }
 
 #define HMC_CUDA(h, call)                                                         \
@@ -490,6 +520,7 @@ extern "C" int gi_hmc_create(const gi_hmc_config *cfg, const double *G, const do
     h->cfg = *cfg;
     h->G = G;
     h->stream = (cudaStream_t)stream;
+    h->fused_state = -1;
     rc = gi_plan_create(cfg->N, cfg->M, cfg->ld, 1, &h->plan);
     if (rc) { delete h; return rc; }
     const size_t bm = sizeof(double) * cfg->ld, bn = sizeof(double) * cfg->N;
@@ -580,6 +611,18 @@ static int grad_eval_and_update(gi_hmc *h, const double *x_in, const double *mw_
                                                      h->cfg.fixed ? h->fix : nullptr, h->dobs_c,
                                                      h->r, h->sums);
         h->launches += (h->wv_kind == 1 ? 2 : 7);
+    } else if (fused_ready(h)) {
+        // d, Aw^T r in ONE pass over Aw (fused.cu); then U_data from d, and the usual fused update
+        rc = gi_fused_pass(h->fused, mw_in, h->dobs_c, h->cfg.fixed ? h->fix : nullptr, h->d, h->gfused, s);
+        if (rc) return rc;
+        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, p->nrows, h->d,
+                                                     h->cfg.fixed ? h->fix : nullptr, h->dobs_c,
+                                                     h->r, h->sums);
+        GI_LAUNCH_CHECK();
+        rc = launch_update(p, &h->cfg.reg, nullptr, h->gfused, 1, x_in, mw_in, h->mwapr, h->wmsq, h->low,
+                           h->high, h->p, x_out, mw_out, grad_out, pcoef, dt, advance, h->sums, s);
+        h->launches += 3;
+        return rc;
     } else {
         rc = launch_fwd_partial(p, h->G, mw_in, s);
         if (rc) return rc;

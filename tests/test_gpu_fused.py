@@ -1,0 +1,82 @@
+"""GPU parity of the single-pass gradient evaluation (gi_fused_pass, csrc/fused.cu): one pass over the
+kernel yields d = G x and g = G^T r with r = (d + fix - mean(d + fix)) - dobs_c (potential.py:698-708).
+Checked against numpy on ragged shapes (strips that do not fill every SM, fewer rows than ring
+slots), against the two-pass kernels, and for bitwise reproducibility; the sampler-level parity with
+the path forced on runs in test_chain_matches_reference_with_fused_pass."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from gravinv3dhmc_b200 import _lib  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def nrm(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("n,m,use_fix", [(1, 1, False), (2, 40, True), (3, 33, False), (5, 5000, True),
+                                         (300, 5000, False), (257, 70001, True), (1000, 200000, True)])
+def test_fused_pass_vs_numpy(n, m, use_fix):
+    L = _lib.lib()
+    rng = np.random.RandomState(n + 7 * m)
+    ld = _lib.padded_ld(m)
+    A = rng.standard_normal((n, m)) * (1.0 + rng.rand(m))[None, :]
+    x = rng.standard_normal(m)
+    dobs_c = rng.standard_normal(n)
+    fix = rng.standard_normal(n) if use_fix else None
+    f64 = dict(dtype=torch.float64, device="cuda")
+    Ad = torch.zeros((n, ld), **f64)
+    Ad[:, :m] = torch.as_tensor(A)
+    xd = torch.zeros(ld, **f64)
+    xd[:m] = torch.as_tensor(x)
+    dd, fd = torch.as_tensor(dobs_c).cuda(), (None if fix is None else torch.as_tensor(fix).cuda())
+    d, g = torch.full((n,), np.nan, **f64), torch.full((ld,), np.nan, **f64)
+    s = _lib.stream_ptr()
+    fh = C.c_void_p()
+    _lib.check(L.gi_fused_create(n, m, ld, _lib.ptr(Ad), s, C.byref(fh)), "gi_fused_create")
+    d_ref = A @ x
+    dinv = d_ref + (fix if use_fix else 0.0)
+    r_ref = (dinv - dinv.mean()) - dobs_c
+    g_ref = A.T @ r_ref
+    def sequence(handle):
+        outs = []
+        for rep in range(3):  # the first pass forms e around 0, the later ones around the previous mean
+            _lib.check(L.gi_fused_pass(handle, _lib.ptr(xd), _lib.ptr(dd), _lib.ptr(fd), _lib.ptr(d),
+                                       _lib.ptr(g), s))
+            d1, g1 = d.cpu().numpy(), g.cpu().numpy()
+            assert nrm(d1, d_ref) < 1e-13
+            assert nrm(g1[:m], g_ref) < (1e-10 if rep == 0 else 1e-12)
+            assert np.all(g1[m:] == 0)
+            outs.append((d1, g1))
+        return outs
+
+    first = sequence(fh)
+    L.gi_fused_destroy(fh)
+    # reproducible: the same sequence of calls on a fresh handle gives the same bits
+    fh2 = C.c_void_p()
+    _lib.check(L.gi_fused_create(n, m, ld, _lib.ptr(Ad), s, C.byref(fh2)), "gi_fused_create")
+    second = sequence(fh2)
+    L.gi_fused_destroy(fh2)
+    for (da, ga), (db, gb) in zip(first, second):
+        assert np.array_equal(da, db) and np.array_equal(ga, gb)
+
+
+def test_chain_matches_reference_with_fused_pass():
+    """the golden single-chain traces (per-leapfrog x and U at 1e-9, identical accept decisions) with
+    the single-pass evaluation forced on for these small kernels (GI_FUSED_GEMV=1 is read when a
+    sampler handle is created, hence the subprocess)"""
+    env = dict(os.environ, GI_FUSED_GEMV="1")
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                          os.path.join(ROOT, "tests", "test_gpu_leapfrog.py"),
+                          "-k", "chain_matches_reference_trace or config1_chain"],
+                         capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
