@@ -86,8 +86,7 @@ SIGNATURES = {
                             _D, _D, C.c_int, _P, _P]),
     "gi_fused_create": (C.c_int, [_I64, _I64, _I64, _P, _P, C.POINTER(_P)]),
     "gi_fused_destroy": (C.c_int, [_P]),
-    "gi_fused_profile": (C.c_int, [_P, _P]),
-    "gi_fused_pass": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "gi_fused_pass": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "gi_hmc_create": (C.c_int, [C.POINTER(HmcConfig), _P, _P, _P, _P, _P, _P, _P, _P,
                                 C.POINTER(_P)]),
     "gi_hmc_destroy": (C.c_int, [_P]),

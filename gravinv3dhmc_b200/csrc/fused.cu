@@ -56,7 +56,7 @@ struct FusedArgs {
     unsigned long long epoch_base;
     double *mean_io;  // [2] mean of the previous / this evaluation (ping-pong by launch parity)
     int mean_slot;
-    long long *dbg;   // optional [8]: clock64 sums per phase (CTA 0, thread 0)
+    int center;       // 1: r = e - mean(e) (potential.py:706); 0: r = e (reginv.py:256, no mean removal)
     double *d_out, *g_out;
 };
 
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
                      : "memory");
     };
     // Iteration i: forward dot of row i (published), then the adjoint update with row j = i - 2.
-    const double m0 = a.mean_io[a.mean_slot];  // last evaluation's mean: e is formed around it, so
+    const double m0 = a.center ? a.mean_io[a.mean_slot] : 0.0;  // last evaluation's mean: e is formed around it, so
     double sd = 0.0;                           // the correction mean' * s below stays small
     unsigned long long pv = 0, ptag = 0;       // prefetched partial of the row consumed NEXT iteration
     for (int64_t i = 0; i < a.nrows + kFLag; ++i) {
@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
         }
     }
     // g = Aw^T e - mean' * s   (r = e - mean', mean' = mean - m0)
-    const double mean = sd * a.inv_n;
-    if (b == 0 && tid == 0) a.mean_io[a.mean_slot ^ 1] = m0 + mean;
+    const double mean = a.center ? sd * a.inv_n : 0.0;
+    if (b == 0 && tid == 0 && a.center) a.mean_io[a.mean_slot ^ 1] = m0 + mean;
 #pragma unroll
     for (int u = 0; u < kFU; ++u) {
         const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
@@ -237,7 +237,6 @@ struct gi_fused {
     size_t smem;
     const double *G;
     double *s, *mean_io;
-    long long *dbg;  // GI_FUSED_PROFILE=1: per-phase clock sums of CTA 0 (diagnostics)
     unsigned long long *part, epoch, nlaunch;
     int64_t launches;
 };
@@ -247,7 +246,6 @@ extern "C" int gi_fused_destroy(gi_fused *f) {
     cudaFree(f->s);
     cudaFree(f->part);
     cudaFree(f->mean_io);
-    cudaFree(f->dbg);
     delete f;
     return GI_OK;
 }
@@ -280,7 +278,6 @@ extern "C" int gi_fused_create(int64_t nrows, int64_t M, int64_t ld, const doubl
     if (e == cudaSuccess) e = cudaMemsetAsync(f->part, 0, 16 * (size_t)nrows * P, st);
     if (e == cudaSuccess) e = cudaMalloc(&f->mean_io, 2 * sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(f->mean_io, 0, 2 * sizeof(double), st);
-    if (e == cudaSuccess && getenv("GI_FUSED_PROFILE")) e = cudaMalloc(&f->dbg, 8 * sizeof(long long));
     if (e != cudaSuccess) {
         gi_fused_destroy(f);
         return cuda_fail(e, "gi_fused_create", __FILE__, __LINE__);
@@ -311,16 +308,8 @@ extern "C" int gi_fused_create(int64_t nrows, int64_t M, int64_t ld, const doubl
     return GI_OK;
 }
 
-// diagnostics: the per-phase clock sums of the last pass (zeros unless GI_FUSED_PROFILE is set)
-extern "C" int gi_fused_profile(gi_fused *f, int64_t *clocks8_host) {
-    GI_REQUIRE(f && clocks8_host, "gi_fused_profile: null pointer");
-    memset(clocks8_host, 0, 8 * sizeof(int64_t));
-    if (f->dbg) GI_CUDA(cudaMemcpy(clocks8_host, f->dbg, 8 * sizeof(long long), cudaMemcpyDeviceToHost));
-    return GI_OK;
-}
-
 extern "C" int gi_fused_pass(gi_fused *f, const double *x_dev, const double *dobs_c_dev, const double *fix_dev,
-                             double *d_dev, double *g_dev, void *stream) {
+                             int32_t center, double *d_dev, double *g_dev, void *stream) {
     GI_REQUIRE(f && x_dev && dobs_c_dev && d_dev && g_dev, "gi_fused_pass: null pointer");
     FusedArgs a;
     a.G = f->G; a.ld = f->ld; a.nrows = f->nrows; a.W = f->W;
@@ -328,8 +317,8 @@ extern "C" int gi_fused_pass(gi_fused *f, const double *x_dev, const double *dob
     a.inv_n = 1.0 / (double)f->nrows;
     a.part = f->part; a.epoch_base = f->epoch;
     a.mean_io = f->mean_io; a.mean_slot = (int)(f->nlaunch & 1ull);
-    a.dbg = f->dbg;
-    f->nlaunch += 1;
+    a.center = center ? 1 : 0;
+    if (center) f->nlaunch += 1;
     a.d_out = d_dev; a.g_out = g_dev;
     f->epoch += (unsigned long long)f->nrows + 1ull;
     void *args[] = {&a};

@@ -613,7 +613,7 @@ static int grad_eval_and_update(gi_hmc *h, const double *x_in, const double *mw_
         h->launches += (h->wv_kind == 1 ? 2 : 7);
     } else if (fused_ready(h)) {
         // d, Aw^T r in ONE pass over Aw (fused.cu); then U_data from d, and the usual fused update
-        rc = gi_fused_pass(h->fused, mw_in, h->dobs_c, h->cfg.fixed ? h->fix : nullptr, h->d, h->gfused, s);
+        rc = gi_fused_pass(h->fused, mw_in, h->dobs_c, h->cfg.fixed ? h->fix : nullptr, 1, h->d, h->gfused, s);
         if (rc) return rc;
         data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, p->nrows, h->d,
                                                      h->cfg.fixed ? h->fix : nullptr, h->dobs_c,

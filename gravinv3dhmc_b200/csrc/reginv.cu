@@ -18,6 +18,7 @@
 // kstep, norms) stay on the device; the host reads one 4-byte "columns still active" word per
 // iteration for the reference's early stop.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -388,6 +389,11 @@ struct gi_cg {
     int *nactive_dev, *nactive_host;
     int32_t hist_maxk;
     int64_t launches;
+    // single-pass data term (fused.cu): D = Aw mw and Gt = Aw^T (D - dobs) in ONE pass over Aw, so an
+    // iteration streams Aw twice (Aw Iw, then this) instead of three times.  -1 not tried, 0 off, 1 on
+    int fused_state;
+    gi_fused *fused;
+    bool gt_valid;  // Gt already holds Aw^T r of the current point
     // wavelet-compressed forward of the data terms (gi_cg_set_wavelet; 0 = off)
     int wv_kind, wv_nz, wv_ny, wv_nx;
     const int64_t *wv_indptr;
@@ -401,6 +407,23 @@ struct gi_cg {
     gi_cg_hook hook;
     void *hook_user;
 };
+
+// plain single-column problems on kernels >= 1 GB (GI_FUSED_GEMV=1 forces, =0 disables)
+static bool cg_fused_ready(gi_cg *h) {
+    if (h->cfg.ncols != 1 || h->W || h->hook || h->wv_kind) return false;
+    if (h->fused_state >= 0) return h->fused_state == 1;
+    h->fused_state = 0;
+    const char *env = getenv("GI_FUSED_GEMV");
+    if (env && env[0] == '0') return false;
+    const bool force = env && env[0] == '1';
+    if (!force && (double)h->cfg.N * (double)h->cfg.ld * 8.0 < 1e9) return false;
+    if (gi_fused_create(h->cfg.N, h->cfg.M, h->cfg.ld, h->G, h->s, &h->fused) != GI_OK) {
+        h->fused = nullptr;
+        return false;
+    }
+    h->fused_state = 1;
+    return true;
+}
 
 static int cg_reduce(gi_cg *h, int what) {
     if (!h->hook) return GI_OK;
@@ -421,6 +444,7 @@ static void cg_free(gi_cg *h) {
     cudaFree(h->nactive_dev);
     cudaFree(h->red_own);
     cudaFree(h->wv_coef);
+    gi_fused_destroy(h->fused);
     if (h->nactive_host) cudaFreeHost(h->nactive_host);
     delete h;
 }
@@ -470,6 +494,7 @@ extern "C" int gi_cg_create(const gi_cg_config *cfg, const double *G_dev, const 
     alloc(&h->red_own, sizeof(double) * C);
     h->red = h->red_own;
     h->n_total = cfg->N;
+    h->fused_state = -1;
     if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int) * C);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->counter, 0, sizeof(unsigned int) * C, h->s);
     if (e == cudaSuccess) e = cudaMalloc(&h->nactive_dev, sizeof(int));
@@ -538,6 +563,13 @@ extern "C" int gi_cg_destroy(gi_cg *h) {
 // (reginv.py:248-269), which go through the wavelet-compressed kernel when one is set -- the step
 // length's Aw @ Iw (reginv.py:425) and the final A @ model_inv (:490) stay dense, as in the reference.
 static int cg_forward(gi_cg *h, const double *X, bool data_term = false) {
+    if (data_term && cg_fused_ready(h)) {
+        // r = d - dobs without mean removal (reginv.py:256): center = 0
+        h->launches += 1;
+        h->gt_valid = true;
+        return gi_fused_pass(h->fused, X, h->dobs, nullptr, 0, h->D, h->Gt, h->s);
+    }
+    h->gt_valid = false;
     if (data_term && h->wv_kind) {
         int rc = h->wv_kind == 1
                      ? gi_dwt_db4_l2_1d(X, h->cfg.M, h->wv_coef, nullptr, h->s)
@@ -553,6 +585,10 @@ static int cg_forward(gi_cg *h, const double *X, bool data_term = false) {
 
 // Gt = Aw^T R, summed over the row shards
 static int cg_adjoint(gi_cg *h) {
+    if (h->gt_valid) {  // the single-pass data term of the previous step already produced it
+        h->gt_valid = false;
+        return GI_OK;
+    }
     double *gt = h->gt_ext ? h->gt_ext : h->Gt;
     int rc;
     if (h->cfg.ncols == 1) { h->launches += 2; rc = gi_gemv_adj(h->plan, h->G, h->R, gt, h->s); }

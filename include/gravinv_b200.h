@@ -211,17 +211,16 @@ int gi_update(gi_plan *plan, const gi_reg_params *reg, const double *gdata_dev,
  * and its adjoint update, using G^T r = G^T e - mean * (G^T 1).  Deterministic; DRAM traffic 8 N M
  * bytes per evaluation.  gi_fused_create fails with GI_ERR_INVALID when the strip of one SM
  * (ld / #SMs columns x 4 slots) does not fit its shared memory -- callers then use gi_gemv_fwd /
- * gi_gemv_adj.  gi_hmc uses it automatically for kernels >= 1 GB (env GI_FUSED_GEMV=0/1 overrides). */
+ * gi_gemv_adj.  gi_hmc and the single-column gi_cg use it automatically for kernels >= 1 GB (env
+ * GI_FUSED_GEMV=0/1 overrides). */
 typedef struct gi_fused gi_fused;
 int gi_fused_create(int64_t nrows, int64_t M, int64_t ld, const double *G_dev, void *stream,
                     gi_fused **out);
 int gi_fused_destroy(gi_fused *f);
-/* diagnostics (env GI_FUSED_PROFILE=1 at create): clock64 sums of CTA 0 over the last pass --
- * [0] row wait, [1] forward dot, [2] own poll, [3] reduction + barrier, [4] adjoint update,
- * [5] barrier, [6] ring refill */
-int gi_fused_profile(gi_fused *f, int64_t *clocks8_host);
+/* center = 1: r = e - mean(e) with e = d + fix - dobs_c (potential.py:699-706); center = 0: r = e
+ * (the residual of inversion/reginv.py:256, 267: no mean removal) */
 int gi_fused_pass(gi_fused *f, const double *x_dev, const double *dobs_c_dev, const double *fix_dev,
-                  double *d_dev, double *g_dev, void *stream);
+                  int32_t center, double *d_dev, double *g_dev, void *stream);
 
 /* ---- single-GPU device-resident sampler --------------------------------------------------- */
 typedef struct gi_hmc gi_hmc;

@@ -50,7 +50,7 @@ def test_fused_pass_vs_numpy(n, m, use_fix):
     def sequence(handle):
         outs = []
         for rep in range(3):  # the first pass forms e around 0, the later ones around the previous mean
-            _lib.check(L.gi_fused_pass(handle, _lib.ptr(xd), _lib.ptr(dd), _lib.ptr(fd), _lib.ptr(d),
+            _lib.check(L.gi_fused_pass(handle, _lib.ptr(xd), _lib.ptr(dd), _lib.ptr(fd), 1, _lib.ptr(d),
                                        _lib.ptr(g), s))
             d1, g1 = d.cpu().numpy(), g.cpu().numpy()
             assert nrm(d1, d_ref) < 1e-13

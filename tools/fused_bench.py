@@ -53,7 +53,7 @@ def main():
     d1, g1 = torch.zeros(n, **f64), torch.zeros(ld, **f64)
 
     def fused():
-        _lib.check(L.gi_fused_pass(fh, _lib.ptr(x), _lib.ptr(dobs_c), _lib.ptr(fix), _lib.ptr(d1), _lib.ptr(g1), s))
+        _lib.check(L.gi_fused_pass(fh, _lib.ptr(x), _lib.ptr(dobs_c), _lib.ptr(fix), 1, _lib.ptr(d1), _lib.ptr(g1), s))
 
     def timed(fn):
         fn()
@@ -78,11 +78,6 @@ def main():
     fused()
     torch.cuda.synchronize()
     out["deterministic"] = bool(torch.equal(d1, d1b) and torch.equal(g1, g1b))
-    if os.environ.get("GI_FUSED_PROFILE"):
-        clk = np.zeros(8, dtype=np.int64)
-        _lib.check(L.gi_fused_profile(fh, _lib.ptr(clk)))
-        names = ["row_wait", "fwd_dot", "own_poll", "reduce_barrier", "adj_update", "barrier", "refill"]
-        out["clocks_per_row"] = {k: round(float(v) / n, 1) for k, v in zip(names, clk)}
     print(json.dumps(out))
     L.gi_fused_destroy(fh)
     L.gi_plan_destroy(plan)
