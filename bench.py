@@ -420,6 +420,19 @@ def gpu_arm(args):
                 "gemv_adj": {"ms": t_adj * 1e3, "GBps": bytes_pass / t_adj / 1e9}}
         dom = "gemv_adj" if t_adj >= t_fwd else "gemv_fwd"
         achieved, peak, unit, bound, peak_src = kern[dom]["GBps"], hbm_peak, "GB/s", "hbm", hbm_src
+        if world == 1 and os.environ.get("GI_FUSED_GEMV", "") != "0":
+            # the single-chain sampler evaluates d and Aw^T r in ONE pass over Aw (csrc/fused.cu): the
+            # dominant kernel of the step.  Algorithmic bytes stay 2 x 8 N M per evaluation (two
+            # products), its DRAM traffic is 8 N M -- so the algorithmic rate may exceed the HBM peak.
+            fh = C.c_void_p()
+            if lib.gi_fused_create(n_local, M, _lib.padded_ld(M), _lib.ptr(eng.Aw), s, C.byref(fh)) == 0:
+                gtmp = eng.vec()
+                t_fu = time_kernel(lambda: _lib.check(lib.gi_fused_pass(
+                    fh, _lib.ptr(xv), _lib.ptr(eng.dobs_c), None, 1, _lib.ptr(eng.d), _lib.ptr(gtmp), s)), reps)
+                lib.gi_fused_destroy(fh)
+                kern["fused_pass"] = {"ms": t_fu * 1e3, "GBps": 2 * bytes_pass / t_fu / 1e9,
+                                      "dram_GBps": bytes_pass / t_fu / 1e9}
+                dom, achieved = "fused_pass", kern["fused_pass"]["GBps"]
     if world > 1:
         t = torch.tensor([achieved], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)

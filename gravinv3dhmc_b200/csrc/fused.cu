@@ -19,7 +19,14 @@
 //                         e * row-strip -- read from SHARED memory, not from HBM -- to its accumulator;
 //                         the slot is then refilled with row i + 2.
 // No atomics (a same-address counter would serialise 148 L2 atomics per row), no grid-wide barrier:
-// a CTA only ever waits for rows published two iterations earlier.  DRAM traffic per evaluation is
+// a CTA only ever waits for rows published two iterations earlier.  What was tried and measured
+// slower on B200 (4096 x 2^20, two-pass 9.5 ms, this kernel 6.8 ms): release/acquire flags instead of
+// tagged pairs (14.7 ms: a MEMBAR per row on the critical path), consuming a row one iteration after
+// its publication (10.9 ms: every poll misses), two CTAs per SM with half strips (10.3 ms: the
+// hand-off traffic grows with the square of the CTA count), a dedicated TMA producer warp with
+// mbarrier slot release (10.5 ms), publishing at the end of the iteration (12.3 ms).  The kernel is
+// bound by the per-row hand-off chain of its single CTA per SM (ncu: short-scoreboard and barrier
+// stalls; DRAM at 62 % of peak), not by bandwidth.  DRAM traffic per evaluation is
 // 8 N M bytes instead of 16 N M; the result is deterministic (fixed strip ownership and summation
 // order).  Rounding differs from the two-pass form at the 1e-16 * |mean s| / |Aw^T r| level (~1e-14),
 // far inside the 1e-9 parity bar of the trajectories.
@@ -42,9 +49,8 @@ constexpr unsigned long long kSpinLimit = 1ull << 26;
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void lds4(unsigned a, double &x0, double &x1, double &x2, double &x3) {
+__device__ __forceinline__ void lds2(unsigned a, double &x0, double &x1) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(a));
-    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(x2), "=d"(x3) : "r"(a + 16));
 }
 
 struct FusedArgs {
@@ -72,14 +78,17 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
     double *scratch = reinterpret_cast<double *>(full + kFS);
     const unsigned ring_a = smem_addr(ring), full_a = smem_addr(full);
 
-    // this thread's slice of x and of the adjoint accumulator: chunk k = tid + 256 u covers strip
-    // columns 4k .. 4k+3
+    // this thread's slice of x and of the adjoint accumulator.  Group u = 1024 strip columns; the
+    // thread owns doubles {2 tid, 2 tid + 1} of the group's first 512 and of its second 512, so a
+    // warp's 16-byte shared-memory loads cover 512 contiguous bytes (conflict free; 32 contiguous
+    // bytes per thread would be 2-way bank conflicts -- 44 % of the wavefronts in the ncu capture)
     double xv[kFU][4], ga[kFU][4];
 #pragma unroll
     for (int u = 0; u < kFU; ++u) {
-        const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
-        if (k4 < Wb) ldg4(a.x + c0 + k4, xv[u][0], xv[u][1], xv[u][2], xv[u][3]);
-        else xv[u][0] = xv[u][1] = xv[u][2] = xv[u][3] = 0.0;
+        const int64_t o0 = 1024LL * u + 2 * tid, o1 = o0 + 512;
+        xv[u][0] = xv[u][1] = xv[u][2] = xv[u][3] = 0.0;
+        if (o0 < Wb) { xv[u][0] = __ldg(a.x + c0 + o0); xv[u][1] = __ldg(a.x + c0 + o0 + 1); }
+        if (o1 < Wb) { xv[u][2] = __ldg(a.x + c0 + o1); xv[u][3] = __ldg(a.x + c0 + o1 + 1); }
         ga[u][0] = ga[u][1] = ga[u][2] = ga[u][3] = 0.0;
     }
     if (tid == 0) {
@@ -137,17 +146,20 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
                     : "=r"(done)
                     : "r"(bar), "r"(parity)
                     : "memory");
-            const unsigned row_a = ring_a + (unsigned)(slot * W * 8);
+            const unsigned row_a = ring_a + (unsigned)(slot * W * 8) + 16u * tid;
 #pragma unroll
             for (int u = 0; u < kFU; ++u) {
-                const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
-                if (k4 < Wb) {
-                    double g0, g1, g2, g3;
-                    lds4(row_a + (unsigned)(k4 * 8), g0, g1, g2, g3);
+                const int64_t o0 = 1024LL * u + 2 * tid;
+                double g0, g1;
+                if (o0 < Wb) {
+                    lds2(row_a + 8192u * u, g0, g1);
                     acc = fma(g0, xv[u][0], acc);
                     acc = fma(g1, xv[u][1], acc);
-                    acc = fma(g2, xv[u][2], acc);
-                    acc = fma(g3, xv[u][3], acc);
+                }
+                if (o0 + 512 < Wb) {
+                    lds2(row_a + 8192u * u + 4096u, g0, g1);
+                    acc = fma(g0, xv[u][2], acc);
+                    acc = fma(g1, xv[u][3], acc);
                 }
             }
         }
@@ -183,17 +195,20 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
             const double dinv = (a.fix ? dj + __ldg(a.fix + j) : dj) - m0;
             const double ej = dinv - __ldg(a.dobs_c + j);
             sd += dinv;
-            const unsigned row_a = ring_a + (unsigned)((int)(j % kFS) * W * 8);
+            const unsigned row_a = ring_a + (unsigned)((int)(j % kFS) * W * 8) + 16u * tid;
 #pragma unroll
             for (int u = 0; u < kFU; ++u) {
-                const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
-                if (k4 < Wb) {
-                    double g0, g1, g2, g3;
-                    lds4(row_a + (unsigned)(k4 * 8), g0, g1, g2, g3);
+                const int64_t o0 = 1024LL * u + 2 * tid;
+                double g0, g1;
+                if (o0 < Wb) {
+                    lds2(row_a + 8192u * u, g0, g1);
                     ga[u][0] = fma(g0, ej, ga[u][0]);
                     ga[u][1] = fma(g1, ej, ga[u][1]);
-                    ga[u][2] = fma(g2, ej, ga[u][2]);
-                    ga[u][3] = fma(g3, ej, ga[u][3]);
+                }
+                if (o0 + 512 < Wb) {
+                    lds2(row_a + 8192u * u + 4096u, g0, g1);
+                    ga[u][2] = fma(g0, ej, ga[u][2]);
+                    ga[u][3] = fma(g1, ej, ga[u][3]);
                 }
             }
             if (tid == 0 && b == (int)(j % P)) a.d_out[j] = dj;
@@ -211,12 +226,14 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
     if (b == 0 && tid == 0 && a.center) a.mean_io[a.mean_slot ^ 1] = m0 + mean;
 #pragma unroll
     for (int u = 0; u < kFU; ++u) {
-        const int64_t k4 = 4 * ((int64_t)tid + kFT * u);
-        if (k4 < Wb) {
-            double s0, s1, s2, s3;
-            ldg4(a.s + c0 + k4, s0, s1, s2, s3);
-            stg4(a.g_out + c0 + k4, ga[u][0] - mean * s0, ga[u][1] - mean * s1, ga[u][2] - mean * s2,
-                 ga[u][3] - mean * s3);
+        const int64_t o0 = 1024LL * u + 2 * tid, o1 = o0 + 512;
+        if (o0 < Wb) {
+            a.g_out[c0 + o0] = ga[u][0] - mean * __ldg(a.s + c0 + o0);
+            a.g_out[c0 + o0 + 1] = ga[u][1] - mean * __ldg(a.s + c0 + o0 + 1);
+        }
+        if (o1 < Wb) {
+            a.g_out[c0 + o1] = ga[u][2] - mean * __ldg(a.s + c0 + o1);
+            a.g_out[c0 + o1 + 1] = ga[u][3] - mean * __ldg(a.s + c0 + o1 + 1);
         }
     }
 }
