@@ -62,14 +62,39 @@ class BlockEngine:
         _lib.check(self.L.gi_plan_create(self.n_local, self.M, self.ld, 1, C.byref(self.plan)),
                    "gi_plan_create")
         self.launches = 0
+        self._fused = None  # single-pass evaluation (csrc/fused.cu): None = not tried, False = unavailable
 
     def __del__(self):
         try:
             if getattr(self, "plan", None):
                 self.L.gi_plan_destroy(self.plan)
                 self.plan = None
+            if getattr(self, "_fused", None):
+                self.L.gi_fused_destroy(self._fused)
+                self._fused = None
         except Exception:
             pass
+
+    def _fused_handle(self):
+        """gi_fused handle over this rank's rows for kernels >= 1 GB (GI_FUSED_GEMV=1 forces it for
+        any shape that fits, =0 disables), plus s = Aw_local^T 1 for the row-sharded mean correction"""
+        if self._fused is None:
+            import os
+
+            self._fused = False
+            env = os.environ.get("GI_FUSED_GEMV", "")
+            big = self.n_local * self.ld * 8.0 >= 1e9
+            if env != "0" and (big or env == "1"):
+                h = C.c_void_p()
+                if self.L.gi_fused_create(self.n_local, self.M, self.ld, _lib.ptr(self.Aw),
+                                          _lib.stream_ptr(), C.byref(h)) == _lib.GI_OK:
+                    self._fused = h
+                    if self.world > 1:
+                        ones = self.torch.ones(self.n_local, dtype=self.torch.float64, device=self.dev)
+                        self._s_local = self.torch.zeros(self.ld, dtype=self.torch.float64, device=self.dev)
+                        _lib.check(self.L.gi_gemv_adj(self.plan, _lib.ptr(self.Aw), _lib.ptr(ones),
+                                                      _lib.ptr(self._s_local), _lib.stream_ptr()), "gi_gemv_adj")
+        return self._fused
 
     def vec(self, a=None):
         """zero-padded device M-vector (ld entries)"""
@@ -89,15 +114,29 @@ class BlockEngine:
         self.d / self.r / self.g / self.sums[0:2].  `dpre` (device, this rank's rows) overrides the
         dense forward product (wavelet-compressed forward, potential.py:693-696)."""
         L, s, p = self.L, _lib.stream_ptr(), _lib.ptr
-        if dpre is not None:
+        fused = self._fused_handle() if dpre is None else False
+        if fused:
+            # d and Aw_local^T (e - mean_local) in ONE pass over this rank's rows
+            _lib.check(L.gi_fused_pass(fused, p(mw), p(self.dobs_c), p(self.fix), 1, p(self.d), p(self.g), s),
+                       "gi_fused_pass")
+        elif dpre is not None:
             self.d.copy_(dpre)
         else:
             _lib.check(L.gi_gemv_fwd(self.plan, p(self.Aw), p(mw), p(self.d), s), "gi_gemv_fwd")
         _lib.check(L.gi_data_sum(self.plan, p(self.d), p(self.fix), p(self.sums), s), "gi_data_sum")
+        if fused and self.world > 1:
+            s0_local = self.sums[0].clone()
         self._all_reduce(self.sums[0:1])
         _lib.check(L.gi_residual(self.plan, p(self.d), p(self.fix), p(self.dobs_c), self.n_total,
                                  p(self.r), p(self.sums), s), "gi_residual")
-        _lib.check(L.gi_gemv_adj(self.plan, p(self.Aw), p(self.r), p(self.g), s), "gi_gemv_adj")
+        if fused:
+            if self.world > 1:
+                # the kernel centred e on the LOCAL mean: move to the global one,
+                # Aw_l^T (e - mean_g) = Aw_l^T (e - mean_l) + (mean_l - mean_g) * Aw_l^T 1
+                delta = s0_local / self.n_local - self.sums[0] / self.n_total
+                self.g.addcmul_(self._s_local, delta.expand_as(self._s_local))
+        else:
+            _lib.check(L.gi_gemv_adj(self.plan, p(self.Aw), p(self.r), p(self.g), s), "gi_gemv_adj")
         if self.world > 1:
             # one exchange: the gradient partials and the partial sum r^2 ride together
             self.gext[self.ld] = self.sums[1]
