@@ -18,7 +18,6 @@ then statistically equivalent but not bit-compatible with numpy's MT19937 stream
 from __future__ import annotations
 
 import ctypes as C
-import os
 import sys
 
 import numpy as np

@@ -19,7 +19,6 @@ What differs by design:
 """
 from __future__ import annotations
 
-import ctypes as C
 import time
 
 import numpy as np

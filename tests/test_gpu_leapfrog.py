@@ -5,7 +5,6 @@ from the unmodified reference (and the CPU oracle on seeded inputs).
 Tolerances (BASELINE.json north_star): per-leapfrog positions and potentials 1e-9 relative, accept
 decisions identical, over the recorded chains; forward data 1e-10."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest

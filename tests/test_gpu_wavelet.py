@@ -5,7 +5,6 @@ the CPU oracle's restatement of the PyWavelets conventions.
 PARITY UNPINNED upstream: PyWavelets is absent from this image and un-pinned by the reference
 (DESIGN.md section 5); what is checked here is CUDA == oracle restatement (1e-12) plus the
 size-independent properties any correct orthonormal transform has."""
-import ctypes as C
 
 import numpy as np
 import pytest
