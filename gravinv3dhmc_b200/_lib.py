@@ -126,6 +126,8 @@ SIGNATURES = {
     "gi_hmcb_leapfrog_steps": (C.c_int, [_P, _P, C.c_int32, _D]),
     "gi_hmcb_launch_count": (_I64, [_P]),
     "gi_hmcb_padded_chains": (C.c_int32, [_P]),
+    "gi_legacy_randn_scaled": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_D), _I64,
+                                         _D, _P]),
     "gi_dwt_db4_l2_1d": (C.c_int, [_P, _I64, _P, C.POINTER(_I64), _P]),
     "gi_dwt_db4_l2_3d": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int32 * 3), _P]),
@@ -224,6 +226,22 @@ def sync():
     import torch as _t
 
     _t.cuda.current_stream().synchronize()
+
+
+def legacy_randn_scaled(rs, n: int, scale: float, out):
+    """out[:n] = rs.randn(n) * scale, bit for bit, for a numpy legacy RandomState `rs` (its state is
+    advanced exactly as numpy would); `out` is a C-contiguous float64 numpy array (e.g. a pinned or
+    shared-memory slot).  ~2x numpy's pace, GIL released."""
+    import numpy as np
+
+    name, key, pos, has_gauss, cached = rs.get_state()
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    c_pos, c_has, c_cached = C.c_int32(int(pos)), C.c_int32(int(has_gauss)), C.c_double(float(cached))
+    check(lib().gi_legacy_randn_scaled(C.c_void_p(key.ctypes.data), C.byref(c_pos), C.byref(c_has),
+                                       C.byref(c_cached), int(n), float(scale), C.c_void_p(out.ctypes.data)),
+          "gi_legacy_randn_scaled")
+    rs.set_state((name, key, c_pos.value, c_has.value, c_cached.value))
+    return out
 
 
 def padded_ld(M: int) -> int:

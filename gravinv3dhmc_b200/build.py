@@ -7,7 +7,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", f) for f in ("assemble.cu", "leapfrog.cu", "batched.cu", "wavelet.cu", "reginv.cu", "sink.cu", "fields.cu", "tess_fields.cu", "fused.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("assemble.cu", "leapfrog.cu", "batched.cu", "wavelet.cu", "reginv.cu", "sink.cu", "fields.cu", "tess_fields.cu", "fused.cu", "hostrng.cu")]
 HDR = [os.path.join(HERE, "csrc", "common.cuh"), os.path.join(HERE, "csrc", "plan.cuh"), os.path.join(HERE, "csrc", "sink.cuh"), os.path.join(HERE, "csrc", "prism_math.cuh"), os.path.join(HERE, "csrc", "tess_math.cuh"), os.path.join(ROOT, "include", "gravinv_b200.h")]
 OUT = os.path.join(HERE, "_build", "libgravinv_b200.so")
 

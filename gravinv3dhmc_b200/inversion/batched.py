@@ -254,7 +254,9 @@ class _DrawAhead:
                     rs = self.streams[c]
                     row = ring.data[c, kk % ring.depth]
                     L = int(rs.randint(self.Lrange[0], self.Lrange[1] + 1))
-                    np.multiply(rs.randn(M), self.Sigma, out=row[:M])
+                    # = rs.randn(M) * Sigma bit for bit (numpy's legacy stream continued in C,
+                    # ~1.3-2x numpy's pace, written straight into the slot)
+                    _lib.legacy_randn_scaled(rs, M, self.Sigma, row[:M])
                     row[M], row[M + 1] = L, float(rs.rand())
                     ring.publish(c, kk)
                     self.produced[c] = kk + 1

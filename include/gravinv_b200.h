@@ -381,6 +381,15 @@ int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t nsteps, dou
 int64_t gi_hmcb_launch_count(const gi_hmcb *h);
 int32_t gi_hmcb_padded_chains(const gi_hmcb *h);
 
+/* ---- host helper: the reference's random stream ---------------------------------------------- */
+/* out_host[i] = randn()_i * scale for the next n normals of a numpy legacy RandomState (MT19937 +
+ * polar method with cached second deviate), bit for bit what `rs.randn(n) * scale` returns, continuing
+ * from -- and writing back -- the generator state `rs.get_state()` exposes (key[624], pos, has_gauss,
+ * cached_gaussian).  The samplers draw momentum in the reference's RNG order (hmc.py:95); this is
+ * ~2x numpy's pace and releases the GIL for the whole vector.  HOST pointers only. */
+int gi_legacy_randn_scaled(uint32_t *key624, int32_t *pos, int32_t *has_gauss, double *cached_gauss,
+                           int64_t n, double scale, double *out_host);
+
 /* ---- wavelet-compressed forward (compressor1D/3D.py) -------------------------------------- */
 /* level-2 db4 periodization DWT of a length-n vector packed like pywt.coeffs_to_array:
  * out = [cA2 | cD2 | cD1], ncoef = len(out) returned through *ncoef (may be called with
