@@ -21,13 +21,16 @@ namespace {
 constexpr int kN = 624, kM = 397;
 constexpr uint32_t kMatrixA = 0x9908b0dfu, kUpper = 0x80000000u, kLower = 0x7fffffffu;
 
+// The generator state is numpy's (raw key[624] + position); outputs are tempered a whole block at a
+// time into a side buffer (two simple loops the host compiler vectorises), which is about twice as
+// fast as tempering word by word behind a position check.
 struct Mt {
     uint32_t *key;
-    int pos;
+    int pos;              // next raw word of the current block (numpy's `pos`)
+    uint32_t buf[kN];     // tempered outputs of the current block, valid for [pos0, kN)
 };
 
-inline void mt_gen(Mt &s) {
-    uint32_t *key = s.key;
+inline void mt_twist(uint32_t *key) {
     int i;
     uint32_t y;
     for (i = 0; i < kN - kM; ++i) {
@@ -40,17 +43,26 @@ inline void mt_gen(Mt &s) {
     }
     y = (key[kN - 1] & kUpper) | (key[0] & kLower);
     key[kN - 1] = key[kM - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrixA);
-    s.pos = 0;
+}
+
+inline void mt_temper(Mt &s, int from) {
+    for (int i = from; i < kN; ++i) {
+        uint32_t y = s.key[i];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        s.buf[i] = y;
+    }
 }
 
 inline uint32_t mt_next(Mt &s) {
-    if (s.pos == kN) mt_gen(s);
-    uint32_t y = s.key[s.pos++];
-    y ^= (y >> 11);
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= (y >> 18);
-    return y;
+    if (s.pos == kN) {
+        mt_twist(s.key);
+        mt_temper(s, 0);
+        s.pos = 0;
+    }
+    return s.buf[s.pos++];
 }
 
 inline double mt_double(Mt &s) {
@@ -65,7 +77,10 @@ extern "C" int gi_legacy_randn_scaled(uint32_t *key624, int32_t *pos, int32_t *h
     GI_REQUIRE(key624 && pos && has_gauss && cached_gauss && (out_host || n == 0) && n >= 0,
                "gi_legacy_randn_scaled: bad argument");
     GI_REQUIRE(*pos >= 0 && *pos <= kN, "gi_legacy_randn_scaled: bad generator position");
-    Mt s{key624, *pos};
+    Mt s;
+    s.key = key624;
+    s.pos = *pos;
+    mt_temper(s, s.pos);
     int have = *has_gauss;
     double cached = *cached_gauss;
     for (int64_t i = 0; i < n; ++i) {
