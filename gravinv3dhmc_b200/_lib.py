@@ -128,6 +128,8 @@ SIGNATURES = {
     "gi_hmcb_padded_chains": (C.c_int32, [_P]),
     "gi_legacy_randn_scaled": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_D), _I64,
                                          _D, _P]),
+    "gi_ring_store_release": (None, [_P, _I64]),
+    "gi_ring_load_acquire": (_I64, [_P]),
     "gi_dwt_db4_l2_1d": (C.c_int, [_P, _I64, _P, C.POINTER(_I64), _P]),
     "gi_dwt_db4_l2_3d": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int32 * 3), _P]),

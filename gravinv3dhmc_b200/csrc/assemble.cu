@@ -324,7 +324,7 @@ scale_columns_kernel(double *__restrict__ G, int64_t nrows, int64_t M, int64_t l
     for (int64_t r = blockIdx.y; r < nrows; r += gridDim.y) {
         double *p = G + r * ld + c4;
         double a0, a1, a2, a3;
-        ldg_stream4(p, a0, a1, a2, a3);
+        ldg4_cg(p, a0, a1, a2, a3);  // coherent load: the same addresses are stored below (.nc is for read-only data)
         stg4(p, __dmul_rn(a0, w[0]), __dmul_rn(a1, w[1]), __dmul_rn(a2, w[2]), __dmul_rn(a3, w[3]));
     }
 }

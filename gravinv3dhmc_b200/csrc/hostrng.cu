@@ -108,3 +108,12 @@ extern "C" int gi_legacy_randn_scaled(uint32_t *key624, int32_t *pos, int32_t *h
     *cached_gauss = cached;
     return GI_OK;
 }
+
+// ---- release / acquire on the shared draw ring's control words (inversion/batched.py: _DrawRing) ----
+// The ring lives in memory mapped by several processes; the payload written before a "ready" /
+// "done" word must be visible to whoever reads that word.  Plain numpy stores only guarantee that on
+// x86 (TSO); these two make it hold on aarch64 hosts (Grace) as well.
+extern "C" void gi_ring_store_release(int64_t *word, int64_t value) {
+    __atomic_store_n(word, value, __ATOMIC_RELEASE);
+}
+extern "C" int64_t gi_ring_load_acquire(const int64_t *word) { return __atomic_load_n(word, __ATOMIC_ACQUIRE); }

@@ -176,29 +176,40 @@ class _DrawRing:
                 self.registered = int(rc) == 0
         self.ready = self.ctl[: nchains * depth].reshape(nchains, depth)
         self.done = self.ctl[nchains * depth:].reshape(world, nchains)
+        # flag words are written with a release store and read with an acquire load (C helpers):
+        # the payload is visible before the flag on every host architecture, not only x86
+        self._st, self._ld = _lib.lib().gi_ring_store_release, _lib.lib().gi_ring_load_acquire
+        self._ctl0 = self.ctl.ctypes.data
         self.data = data.reshape(nchains, depth, M + 2)
         self.tdata = self.tdata.view(nchains, depth, M + 2)
         self.abort = False
 
+    def _ready_addr(self, c, slot):
+        return self._ctl0 + 8 * (c * self.depth + slot)
+
+    def _done_addr(self, r, c):
+        return self._ctl0 + 8 * (self.nc * self.depth + r * self.nc + c)
+
     def writable(self, c, k):
         """may the owner generate proposal k of chain c now?"""
-        return int(self.done[:, c].min()) >= k - self.depth + 1
+        return min(int(self._ld(self._done_addr(r, c))) for r in range(self.world)) >= k - self.depth + 1
 
     def publish(self, c, k):
-        self.ready[c, k % self.depth] = k + 1  # after the payload (x86 stores are not reordered)
+        self._st(self._ready_addr(c, k % self.depth), k + 1)  # release: after the payload
 
     def wait_ready(self, c, k):
         import time
 
         pause = 20e-6
-        while int(self.ready[c, k % self.depth]) != k + 1:
+        addr = self._ready_addr(c, k % self.depth)
+        while int(self._ld(addr)) != k + 1:  # acquire: the payload is visible once the flag is
             if self.abort:
                 raise RuntimeError("draw ring closed")
             time.sleep(pause)
             pause = min(pause * 1.5, 1e-3)
 
     def release(self, c, k):
-        self.done[self.rank, c] = k + 1
+        self._st(self._done_addr(self.rank, c), k + 1)
 
     def close(self):
         self.abort = True

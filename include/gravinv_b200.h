@@ -390,6 +390,12 @@ int32_t gi_hmcb_padded_chains(const gi_hmcb *h);
 int gi_legacy_randn_scaled(uint32_t *key624, int32_t *pos, int32_t *has_gauss, double *cached_gauss,
                            int64_t n, double scale, double *out_host);
 
+/* release store / acquire load of one control word of the draw ring that the ranks of a node share
+ * through mapped host memory (payload before flag on every host architecture, not only x86).  HOST
+ * pointers only. */
+void gi_ring_store_release(int64_t *word, int64_t value);
+int64_t gi_ring_load_acquire(const int64_t *word);
+
 /* ---- wavelet-compressed forward (compressor1D/3D.py) -------------------------------------- */
 /* level-2 db4 periodization DWT of a length-n vector packed like pywt.coeffs_to_array:
  * out = [cA2 | cD2 | cD1], ncoef = len(out) returned through *ncoef (may be called with
