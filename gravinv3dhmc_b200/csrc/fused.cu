@@ -11,8 +11,8 @@
 // [b W, (b+1) W) for every row: its slice of x and of the adjoint accumulator live in registers.
 // Rows stream through a 4-slot shared-memory ring filled by 1-D TMA bulk copies
 // (cp.async.bulk ... mbarrier::complete_tx), ~2 rows (2 x 56 KB at M = 2^20) in flight per SM.
-//   phase 1 (row i)     : partial dot of the strip with x, published as a 16-byte {value, tag} pair
-//                         in ONE vector store (no fence, no flag);
+//   phase 1 (row i)     : partial dot of the strip with x, published as two self-validating 8-byte
+//                         words {value bits 0..31 | tag, value bits 32..63 | tag} (no fence, no flag);
 //   phase 2 (row i - 2) : every CTA polls the 148 pairs of that row (the poll is issued an iteration
 //                         early, its L2 round trip hides under the arithmetic), sums them in a fixed
 //                         order (identical bits on every CTA), forms e and adds
@@ -58,7 +58,7 @@ struct FusedArgs {
     int64_t ld, nrows, W;
     const double *x, *dobs_c, *fix, *s;
     double inv_n;
-    unsigned long long *part;     // [nrows][P] {value bits, tag = epoch_base + row + 1}
+    unsigned long long *part;     // [nrows][P][2] {value lo32 | tag << 32, value hi32 | tag << 32}, tag = epoch_base + row + 1 (mod 2^32)
     unsigned long long epoch_base;
     double *mean_io;  // [2] mean of the previous / this evaluation (ping-pong by launch parity)
     int mean_slot;
@@ -115,25 +115,29 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
     if (tid == 0)
         for (int64_t r = 0; r < kFS && r < a.nrows; ++r) issue(r);
 
-    // Partials travel as 16-byte {value, tag} pairs written with ONE vector store and polled with ONE
-    // vector load (no fence, no separate flag: aligned 16-byte accesses are single transactions, the
-    // protocol NCCL's LL128 also builds on); tag = epoch_base + row + 1 never repeats across launches.
+    // Partials travel as TWO self-validating 8-byte words, {value bits 0..31 | tag << 32} and
+    // {value bits 32..63 | tag << 32} (the protocol of NCCL's LL): PTX guarantees single-copy atomicity
+    // for an aligned 8-byte scalar -- and a vector access is a set of such scalars, with no ordering
+    // or 16-byte atomicity between them -- so each word carries its own 32-bit tag and a value is
+    // accepted only when BOTH words show the tag of the row.  No fence, no separate flag.  A slot's
+    // previous occupant is always the previous launch's word for the same row (every launch rewrites
+    // every slot), whose tag differs by nrows + 1 (mod 2^32) != 0, so a stale word can never pass.
     // The poll for row j is issued one iteration early and only CHECKED when the row is consumed, so
     // its L2 round trip hides under the arithmetic of the rows in between.
-    auto poll = [&](int64_t row, unsigned long long &v, unsigned long long &tag) {
+    auto poll = [&](int64_t row, unsigned long long &w0, unsigned long long &w1) {
         asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];"
-                     : "=l"(v), "=l"(tag)
+                     : "=l"(w0), "=l"(w1)
                      : "l"(a.part + 2 * (row * P + tid))
                      : "memory");
     };
     // Iteration i: forward dot of row i (published), then the adjoint update with row j = i - 2.
     const double m0 = a.center ? a.mean_io[a.mean_slot] : 0.0;  // last evaluation's mean: e is formed around it, so
     double sd = 0.0;                           // the correction mean' * s below stays small
-    unsigned long long pv = 0, ptag = 0;       // prefetched partial of the row consumed NEXT iteration
+    unsigned long long pw0 = 0, pw1 = 0;       // prefetched words of the row consumed NEXT iteration
     for (int64_t i = 0; i < a.nrows + kFLag; ++i) {
         const int64_t j = i - kFLag;
-        unsigned long long cv = pv, ctag = ptag;  // partial of row j, polled during iteration i - 1
-        if (tid < P && j + 1 >= 0 && j + 1 < a.nrows) poll(j + 1, pv, ptag);
+        unsigned long long cw0 = pw0, cw1 = pw1;  // words of row j, polled during iteration i - 1
+        if (tid < P && j + 1 >= 0 && j + 1 < a.nrows) poll(j + 1, pw0, pw1);
         double acc = 0.0;
         if (i < a.nrows) {
             // ---- phase 1: partial dot product of row i with this CTA's slice of x ------------
@@ -166,13 +170,13 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
         double v = 0.0;
         if (j >= 0 && tid < P) {
             // the complete row j: this thread's share is CTA `tid`'s partial
-            const unsigned long long target = a.epoch_base + (unsigned long long)j + 1ull;
+            const unsigned long long target = (a.epoch_base + (unsigned long long)j + 1ull) & 0xffffffffull;
             unsigned long long spins = 0;
-            while (ctag != target) {
-                poll(j, cv, ctag);
+            while ((cw0 >> 32) != target || (cw1 >> 32) != target) {
+                poll(j, cw0, cw1);
                 if (++spins > kSpinLimit) __trap();
             }
-            v = __longlong_as_double((long long)cv);
+            v = __longlong_as_double((long long)((cw0 & 0xffffffffull) | (cw1 << 32)));
         }
         // one block-wide reduction for both: acc -> this CTA's partial of row i (thread 0 publishes),
         // v -> d_j in a fixed order (identical bits on every CTA)
@@ -183,9 +187,10 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
         if (tid == 0 && i < a.nrows) {
             double t = 0.0;
             for (int w = 0; w < kFT / 32; ++w) t += scratch[w];
-            const unsigned long long tag = a.epoch_base + (unsigned long long)i + 1ull;
+            const unsigned long long tag = (a.epoch_base + (unsigned long long)i + 1ull) << 32;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
             asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(a.part + 2 * (i * P + b)),
-                         "l"((unsigned long long)__double_as_longlong(t)), "l"(tag)
+                         "l"((bits & 0xffffffffull) | tag), "l"((bits >> 32) | tag)
                          : "memory");
         }
         if (j >= 0) {

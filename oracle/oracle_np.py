@@ -294,6 +294,52 @@ def tess_leaves(lon, lat, height, bounds, ratio=RATIO_G, threads: int = 1):
     return out
 
 
+_QLIB = None
+
+
+def build_quad(force: bool = False) -> str:
+    """liboracle_quad.so: the binary128 (libquadmath) leaf evaluation of oracle_tess_quad.c"""
+    so = os.path.join(HERE, "_build", "liboracle_quad.so")
+    src = os.path.join(HERE, "csrc", "oracle_tess_quad.c")
+    if force or not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", so,
+                               "-lquadmath", "-lm"])
+    return so
+
+
+def tess_gz_pairs_quad(lon, lat, height, bounds, obs_idx, cell_idx, ratio=RATIO_G, threads: int = 1):
+    """(values, leaves) for the listed (observation, cell) pairs: the reference's subdivision (FP64
+    decisions, identical leaves) with every leaf's GLQ sum and the accumulation in binary128, rounded
+    to FP64 at the end and scaled like kernel2d (tesseroid.py:430) -- the "exact" value of the same
+    quadrature, against which FP64 implementations are compared on the near field."""
+    global _QLIB
+    if _QLIB is None:
+        _QLIB = ctypes.CDLL(build_quad())
+        dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)
+        _QLIB.oracle_tess_gz_pairs_quad.argtypes = [dp, dp, dp, dp, ip, dp, ip, ctypes.c_int64,
+                                                    ctypes.c_double, ctypes.c_double, ctypes.c_double, dp,
+                                                    ctypes.c_void_p]
+        _QLIB.oracle_tess_gz_pairs_quad.restype = None
+    bounds = _c(bounds).reshape(-1, 6)
+    lonr, sinlat, coslat, radius = (_c(a) for a in convert_coords(_c(lon), _c(lat), _c(height)))
+    obs_idx = np.ascontiguousarray(obs_idx, dtype=np.int64)
+    cell_idx = np.ascontiguousarray(cell_idx, dtype=np.int64)
+    n = obs_idx.size
+    out, leaves = np.zeros(n), np.zeros(n, dtype=np.int32)
+    ip = ctypes.POINTER(ctypes.c_int64)
+
+    def run(lo, hi):
+        if hi > lo:
+            _QLIB.oracle_tess_gz_pairs_quad(_dp(lonr), _dp(sinlat), _dp(coslat), _dp(radius),
+                                            obs_idx[lo:hi].ctypes.data_as(ip), _dp(bounds),
+                                            cell_idx[lo:hi].ctypes.data_as(ip), hi - lo, ratio, SI2MGAL, G,
+                                            _dp(out[lo:hi]), leaves[lo:hi].ctypes.data_as(ctypes.c_void_p))
+
+    _run_rows(run, n, threads)
+    return out, leaves
+
+
 def _run_rows(fn, N, threads):
     if threads <= 1:
         fn(0, N)

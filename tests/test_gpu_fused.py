@@ -70,6 +70,43 @@ def test_fused_pass_vs_numpy(n, m, use_fix):
         assert np.array_equal(da, db) and np.array_equal(ga, gb)
 
 
+def test_fused_pass_stress_vs_two_pass():
+    """600 back-to-back launches with a changing x on a kernel that fills every SM (148 CTAs exchanging
+    2048 rows of partials per launch): d must equal the two-pass forward to rounding and g the
+    two-pass adjoint of the same residual, every time -- a torn or stale {value, tag} word (ADVICE r1:
+    the hand-off words are self-validating since round 2) would show up as an O(1) error."""
+    L = _lib.lib()
+    n, m = 2048, 148 * 512
+    ld = _lib.padded_ld(m)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(5)
+    A = torch.zeros((n, ld), **f64)
+    A[:, :m] = torch.randn((n, m), generator=gen, **f64)
+    dobs_c = torch.randn(n, generator=gen, **f64)
+    s = _lib.stream_ptr()
+    fh, plan = C.c_void_p(), C.c_void_p()
+    _lib.check(L.gi_fused_create(n, m, ld, _lib.ptr(A), s, C.byref(fh)), "gi_fused_create")
+    _lib.check(L.gi_plan_create(n, m, ld, 1, C.byref(plan)), "gi_plan_create")
+    x = torch.zeros(ld, **f64)
+    d, g = torch.zeros(n, **f64), torch.zeros(ld, **f64)
+    d2, g2, r2 = torch.zeros(n, **f64), torch.zeros(ld, **f64), torch.zeros(n, **f64)
+    worst_d = worst_g = 0.0
+    for it in range(600):
+        x[:m] = torch.randn(m, generator=gen, **f64)
+        _lib.check(L.gi_fused_pass(fh, _lib.ptr(x), _lib.ptr(dobs_c), None, 1, _lib.ptr(d), _lib.ptr(g), s))
+        if it % 4:   # most launches run back to back (the next launch reuses the partial slots)
+            continue
+        _lib.check(L.gi_gemv_fwd(plan, _lib.ptr(A), _lib.ptr(x), _lib.ptr(d2), s))
+        r2.copy_((d2 - d2.mean()) - dobs_c)
+        _lib.check(L.gi_gemv_adj(plan, _lib.ptr(A), _lib.ptr(r2), _lib.ptr(g2), s))
+        worst_d = max(worst_d, float((d - d2).abs().max() / d2.abs().max()))
+        worst_g = max(worst_g, float((g - g2).abs().max() / g2.abs().max()))
+    L.gi_fused_destroy(fh)
+    L.gi_plan_destroy(plan)
+    assert worst_d < 1e-13 and worst_g < 1e-11, (worst_d, worst_g)
+
+
 def test_chain_matches_reference_with_fused_pass():
     """the golden single-chain traces (per-leapfrog x and U at 1e-9, identical accept decisions) with
     the single-pass evaluation forced on for these small kernels (GI_FUSED_GEMV=1 is read when a
