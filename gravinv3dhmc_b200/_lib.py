@@ -117,6 +117,15 @@ SIGNATURES = {
     "gi_hmcb_propose": (C.c_int, [_P, _P, _P, _D, _P, _P, _P, _P]),
     "gi_hmcb_propose_philox": (C.c_int, [_P, C.c_uint64, C.c_uint64, _D, _P, _D, _P]),
     "gi_hmcb_set_shard": (C.c_int, [_P, _I64, _P, _P, C.c_int32, _P, _P, _P]),
+    "gi_peer_create": (C.c_int, [C.c_int32, C.c_int32, _I64, C.POINTER(_P)]),
+    "gi_peer_export": (C.c_int, [_P, _P]),
+    "gi_peer_connect": (C.c_int, [_P, _P]),
+    "gi_peer_destroy": (C.c_int, [_P]),
+    "gi_peer_bytes_sent": (_I64, [_P]),
+    "gi_peer_allreduce_small": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "gi_hmcb_peer_bytes": (_I64, [_P, C.c_int32]),
+    "gi_hmcb_set_peer": (C.c_int, [_P, _P, _I64, _P]),
+    "gi_hmcb_owned_columns": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "gi_hmcb_stream_begin": (C.c_int, [_P, _D]),
     "gi_hmcb_stream_feed": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _P]),
     "gi_hmcb_stream_feed_dev": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _P]),

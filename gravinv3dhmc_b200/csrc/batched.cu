@@ -29,6 +29,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "peer.cuh"
 #include "plan.cuh"
 #include "sink.cuh"
 
@@ -123,7 +124,8 @@ __host__ __device__ constexpr int adj_stage_bytes() { return kAdjK * kAdjCols * 
 template <int NT, int WC>
 __global__ void __launch_bounds__(kGemmThreads * WC, 1)
 gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ X, int64_t nrows,
-                int64_t kchunk, int64_t rowblocks, double *__restrict__ part) {
+                int64_t kchunk, int64_t rowblocks, double *__restrict__ part, int64_t nkc, int64_t kc_rot,
+                PeerWait pw, PeerMap pm) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = kGemmThreads * WC;
     constexpr int C = 8 * NT;
@@ -137,10 +139,28 @@ gemm_fwd_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int wr = warp & 7, wc = warp >> 3;
     const int64_t tile = blockIdx.x;
-    const int64_t kc = tile / rowblocks, rb = tile - kc * rowblocks;
+    // peer mode: the k-chunks inside this rank's own column slice come first, the others in the
+    // order their X slices arrive (kc_rot = first chunk that starts inside the own slice)
+    const int64_t kslot = tile / rowblocks, rb = tile - kslot * rowblocks;
+    const int64_t kc = (kslot + kc_rot) % nkc;
     const int64_t r0 = rb * kFwdRows;
     const int64_t c0 = kc * kchunk, c1 = min(c0 + kchunk, ld);
     const int ntiles = (int)((c1 - c0) / kFwdK);
+    if (pw.epoch) {
+        // the X columns of the other ranks' slices are pushed into this buffer by their copy engines;
+        // flag[q] >= epoch says slice q of this evaluation's positions has landed (peer.cuh)
+        if (tid == 0) {
+            for (int q = 0; q < pm.nranks; ++q) {
+                if (q == pm.me || pm.col[q + 1] <= pm.col[q] || pm.col[q] >= c1 || pm.col[q + 1] <= c0) continue;
+                unsigned long long v, spins = 0;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(pw.flag + q) : "memory");
+                    if (++spins > (1ull << 27)) __trap();
+                } while (v < pw.epoch);
+            }
+        }
+        __syncthreads();
+    }
 
     // this thread's copy slots: Aw rows tid/CPR + RPP*u, 16-B chunk tid%CPR (swizzled by row parity)
     const int lrow = tid / CPR, lch = tid % CPR;
@@ -263,7 +283,7 @@ template <int NT, int WC>
 __global__ void __launch_bounds__(kGemmThreads * WC, 1)
 gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restrict__ R, int64_t npad,
                 int64_t nrows, double *__restrict__ out, int64_t strip0, int64_t out_ld,
-                int64_t out_col0) {
+                int64_t out_col0, PeerOut po, PeerMap pm) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = kGemmThreads * WC;
     constexpr int C = 8 * NT;
@@ -390,6 +410,16 @@ gemm_adj_kernel(const double *__restrict__ G, int64_t ld, const double *__restri
 #endif
     }
     cp_async_wait<0>();
+    if (pm.nranks) {
+        // peer mode: this strip's tile goes straight into its OWNER rank's staging block over NVLink
+        // ([source rank][chain][owned columns]; a strip never straddles two slices) -- the
+        // reduce-scatter of the gradient partials, spread over the whole contraction
+        int o = 0;
+        while (o + 1 < pm.nranks && v0 >= pm.col[o + 1]) ++o;
+        out = po.stage[o] + (int64_t)pm.me * po.src_stride;
+        out_ld = po.ldp;
+        out_col0 = pm.col[o];
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int64_t v = v0 + 32 * wv + 16 * h + 2 * g;
@@ -489,7 +519,7 @@ __global__ void __launch_bounds__(kUpdThreads) update_batched_kernel(UpdateArgs 
     }
     const int64_t off = c * ctl.vec_stride;
     if (a.grad_in) a.grad_in += off;
-    if (a.gpart) a.gpart += a.gp_ldk ? c * a.gp_ldk : off;
+    if (a.gpart) a.gpart += a.gp_nsrc ? c * a.gp_pitch : (a.gp_ldk ? c * a.gp_ldk : off);
     a.x_in += off;
     a.mw_in += off;
     a.p += off;
@@ -729,12 +759,24 @@ void gi::batched_plan_free(gi_plan *p) {
     cudaFree(p->b_counter);
 }
 
-int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s) {
+int gi::launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s,
+                        unsigned long long wait_epoch) {
     const unsigned grid = (unsigned)(p->b_nkc * p->b_rowblocks);
+    PeerWait pw;
+    PeerMap pm;
+    memset(&pw, 0, sizeof(pw));
+    memset(&pm, 0, sizeof(pm));
+    int64_t kc_rot = 0;
+    if (p->b_peer) {
+        pm = p->b_peer->map;
+        kc_rot = p->b_peer->kc_rot;
+        pw.flag = p->b_peer->xflag;
+        pw.epoch = wait_epoch;
+    }
 #define GI_FWD(NT)                                                                             \
     gemm_fwd_kernel<NT, WarpSplit<NT>::fwd>                                                    \
         <<<grid, kGemmThreads * WarpSplit<NT>::fwd, kStages * fwd_stage_bytes<NT>() + kMbarBytes, s>>>(     \
-        G, p->ld, X, p->nrows, p->b_kchunk, p->b_rowblocks, p->b_part)
+        G, p->ld, X, p->nrows, p->b_kchunk, p->b_rowblocks, p->b_part, p->b_nkc, kc_rot, pw, pm)
     switch (p->b_nt) {
         case 1: GI_FWD(1); break;
         case 2: GI_FWD(2); break;
@@ -757,12 +799,20 @@ int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *ou
     const int64_t strips = npieces == 1 ? p->b_strips : ldk / kAdjCols;
     const int64_t strip0 = piece * strips;
     const unsigned grid = (unsigned)strips;
-    double *outp = out + (int64_t)piece * p->b_C * ldk;
+    double *outp = out ? out + (int64_t)piece * p->b_C * ldk : nullptr;
     const int64_t col0 = piece * ldk;
+    PeerOut po;
+    PeerMap pm;
+    memset(&po, 0, sizeof(po));
+    memset(&pm, 0, sizeof(pm));
+    if (p->b_peer) {  // the epilogue stores every strip's tile into its owner's staging block
+        po = p->b_peer->out;
+        pm = p->b_peer->map;
+    }
 #define GI_ADJ(NT)                                                                             \
     gemm_adj_kernel<NT, WarpSplit<NT>::adj>                                                    \
         <<<grid, kGemmThreads * WarpSplit<NT>::adj, kStages * adj_stage_bytes<NT>() + kMbarBytes, s>>>(     \
-        G, p->ld, R, p->b_npad, p->nrows, outp, strip0, ldk, col0)
+        G, p->ld, R, p->b_npad, p->nrows, outp, strip0, ldk, col0, po, pm)
     switch (p->b_nt) {
         case 1: GI_ADJ(1); break;
         case 2: GI_ADJ(2); break;
@@ -776,6 +826,25 @@ int gi::launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *ou
 #undef GI_ADJ
     GI_LAUNCH_CHECK();
     return GI_OK;
+}
+
+// peer mode: restrict an update launch to this rank's column slice and point its data gradient at the
+// staged partials of all source ranks; returns the number of CTAs along x (0: empty slice)
+static int64_t peer_slice(const gi_plan *p, UpdateArgs &a, bool from_partials) {
+    if (!p->b_peer) return p->upd_blocks;
+    const PeerLaunch &pl = *p->b_peer;
+    a.col0 = pl.map.col[pl.map.me];
+    a.col1 = pl.map.col[pl.map.me + 1];
+    const int64_t hi = std::min<int64_t>(a.col1, p->M);
+    if (hi <= a.col0) return 0;
+    if (from_partials) {
+        a.gpart = pl.stage_local;
+        a.gp_nsrc = pl.map.nranks;
+        a.gp_src_stride = pl.out.src_stride;
+        a.gp_pitch = pl.out.ldp;
+        a.gp_ldk = 0;
+    }
+    return ceil_div(hi - a.col0, (int64_t)kUpdThreads * kUpdVec * 4);
 }
 
 int gi::launch_misfit_batched(gi_plan *p, int mode, int64_t n_total, double *d, const double *fix,
@@ -804,7 +873,9 @@ int gi::launch_update_batched(gi_plan *p, const gi_reg_params *reg, const double
     memset(&ctl, 0, sizeof(ctl));
     ctl.L = L_dev; ctl.step = step; ctl.uniform_mode = uniform_mode; ctl.vec_stride = p->ld;
     ctl.nblocks = p->upd_blocks;
-    dim3 grid((unsigned)p->upd_blocks, (unsigned)p->b_C);
+    const int64_t blocks = peer_slice(p, a, gdata != nullptr);
+    if (blocks == 0) return GI_OK;  // this rank owns no columns
+    dim3 grid((unsigned)blocks, (unsigned)p->b_C);
     update_batched_kernel<<<grid, kUpdThreads, 0, s>>>(a, ctl);
     GI_LAUNCH_CHECK();
     return GI_OK;
@@ -916,15 +987,31 @@ struct gi_hmcb {
     // on-device sample sink (gi_hmcb_attach_stats): chain c -> slot c
     gi_stats *stats;
     const double *stats_scale;
+    // peer-memory exchange (gi_hmcb_set_peer, peer.cuh): replaces the hook path
+    gi_peer *peer;
+    PeerLaunch pl;
+    double *sums_part;                 // [C][8] this rank's partial Um / K sums of the last update
+    unsigned long long *xepoch_src;    // [8] local ring: the epoch value the copy engines send as X flag
+    unsigned long long xepoch;         // pushes so far; the forward pass waits for flag >= epoch
+    unsigned long long wait_xa, wait_xb;  // epoch that completes the positions held in xa / xb (0: local)
+    cudaStream_t push_stream;
+    cudaEvent_t ev_upd, ev_push;
+    bool push_pending;
+    double *own_xa, *own_xb, *own_mwa, *own_mwb;  // the handle's own buffers, replaced by symmetric ones
+    int64_t peer_steps;
 };
 
 static void hmcb_free(gi_hmcb *h) {
     if (!h) return;
     const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
-    double *bufs[] = {h->x_cur, h->g_cur, h->xa, h->xb, h->p, h->gnew, h->gdata, h->low, h->high,
+    double *bufs[] = {h->x_cur, h->g_cur, h->p, h->gnew, h->gdata, h->low, h->high,
                       h->mwapr, h->wmsq, h->d_cur, h->d, h->r, h->dobs_c, h->fix, h->sums, h->u_dev};
     for (double *b : bufs) cudaFree(b);
-    if (logc) { cudaFree(h->mw_cur); cudaFree(h->mwa); cudaFree(h->mwb); }
+    if (!h->peer) { cudaFree(h->xa); cudaFree(h->xb); }
+    if (logc) {
+        cudaFree(h->mw_cur);
+        if (!h->peer) { cudaFree(h->mwa); cudaFree(h->mwb); }
+    }
     cudaFree(h->L_dev);
     cudaFree(h->st);
     cudaFree(h->qp);
@@ -934,6 +1021,15 @@ static void hmcb_free(gi_hmcb *h) {
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
     if (h->rec_host) cudaFreeHost(h->rec_host);
     if (h->st_host) cudaFreeHost(h->st_host);
+    if (h->peer) {  // xa / xb (mwa / mwb) live in the caller's symmetric buffer; free the originals
+        cudaFree(h->own_xa); cudaFree(h->own_xb);
+        if (logc) { cudaFree(h->own_mwa); cudaFree(h->own_mwb); }
+        cudaFree(h->sums_part);
+        cudaFree(h->xepoch_src);
+        if (h->push_stream) cudaStreamDestroy(h->push_stream);
+        if (h->ev_upd) cudaEventDestroy(h->ev_upd);
+        if (h->ev_push) cudaEventDestroy(h->ev_push);
+    }
     gi_plan_destroy(h->plan);
     delete h;
 }
@@ -1050,15 +1146,98 @@ extern "C" int gi_hmcb_set_reg(gi_hmcb *h, const gi_reg_params *reg) {
     return GI_OK;
 }
 
+// ---- peer mode helpers (peer.cuh) ----------------------------------------------------------------
+// epoch of the push that completes the positions held in `buf` (0: complete locally)
+static unsigned long long hb_wait_epoch(const gi_hmcb *h, const double *buf) {
+    if (!h->peer) return 0;
+    if (buf == h->xa || buf == h->mwa) return h->wait_xa;
+    if (buf == h->xb || buf == h->mwb) return h->wait_xb;
+    return 0;
+}
+
+// before an update launch: the copy engines must be done reading the buffer it is about to rewrite
+static int hb_pre_update(gi_hmcb *h) {
+    if (h->peer && h->push_pending) {
+        GI_CUDA(cudaStreamWaitEvent(h->stream, h->ev_push, 0));
+        h->push_pending = false;
+    }
+    return GI_OK;
+}
+
+// after an update launch: sum the slices' partial Um / K over the ranks (same bits everywhere) and
+// leave the next push's epoch where the copy engines will read it
+static int hb_post_update(gi_hmcb *h) {
+    if (!h->peer) return GI_OK;
+    const unsigned long long next = h->peer->xepoch + 1ull;
+    h->launches += 1;
+    return peer_scalars(h->peer, h->sums_part, h->sums, (int)h->C, 2, 4, h->xepoch_src + (next & 7ull), next,
+                        h->stream);
+}
+
+// all-gather of the freshly updated positions: this rank's column slice of `xbuf` (and of `mwbuf`
+// under the logarithmic constraint) goes to every peer's copy of the buffer on the copy engines of
+// a side stream, nearest reader first, each followed by the 8-byte epoch flag the peer's forward
+// kernel polls; the forward pass of this rank starts at once on its own slice
+static int hb_push(gi_hmcb *h, double *xbuf, double *mwbuf) {
+    if (!h->peer) return GI_OK;
+    gi_peer *pr = h->peer;
+    pr->xepoch += 1ull;
+    const unsigned long long ep = pr->xepoch;
+    const int P = pr->world, me = pr->rank;
+    const int64_t lo = h->pl.map.col[me], w = h->pl.map.col[me + 1] - lo;
+    const size_t pitch = sizeof(double) * h->cfg.ld;
+    if (P > 1) {
+        GI_CUDA(cudaEventRecord(h->ev_upd, h->stream));
+        GI_CUDA(cudaStreamWaitEvent(h->push_stream, h->ev_upd, 0));
+        for (int k = 1; k < P; ++k) {
+            const int q = (me - k + P) % P;  // rank me - 1 reads slice `me` right after its own
+            if (w > 0) {
+                double *dst = reinterpret_cast<double *>(pr->base[q] + (reinterpret_cast<unsigned char *>(xbuf) - pr->base[me]));
+                GI_CUDA(cudaMemcpy2DAsync(dst + lo, pitch, xbuf + lo, pitch, sizeof(double) * w, (size_t)h->C,
+                                          cudaMemcpyDeviceToDevice, h->push_stream));
+                pr->nvlink_bytes += (int64_t)sizeof(double) * w * h->C;
+                if (mwbuf != xbuf) {
+                    dst = reinterpret_cast<double *>(pr->base[q] + (reinterpret_cast<unsigned char *>(mwbuf) - pr->base[me]));
+                    GI_CUDA(cudaMemcpy2DAsync(dst + lo, pitch, mwbuf + lo, pitch, sizeof(double) * w, (size_t)h->C,
+                                              cudaMemcpyDeviceToDevice, h->push_stream));
+                    pr->nvlink_bytes += (int64_t)sizeof(double) * w * h->C;
+                }
+            }
+            unsigned long long *flag = reinterpret_cast<unsigned long long *>(pr->base[q] + kPeerFlagX) + me;
+            GI_CUDA(cudaMemcpyAsync(flag, h->xepoch_src + (ep & 7ull), sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToDevice, h->push_stream));
+        }
+        GI_CUDA(cudaEventRecord(h->ev_push, h->push_stream));
+        h->push_pending = true;
+    }
+    if (xbuf == h->xa) h->wait_xa = ep;
+    else h->wait_xb = ep;
+    return GI_OK;
+}
+
 // d, r, sums[.][0..1] and the gradient partials for the positions mw_in; in row-sharded mode the two
 // exchange steps go through the caller's hook and the adjoint output is reduced piece by piece
-// while the next piece is being computed
+// while the next piece is being computed -- or, in peer mode, through peer memory: the scalars by
+// the slot-table kernel, the gradient partials by the adjoint kernel's own epilogue
 static int hb_data_pass(gi_hmcb *h, const double *mw_in) {
     gi_plan *p = h->plan;
     cudaStream_t s = h->stream;
     const double *fix = h->cfg.fixed ? h->fix : nullptr;
-    int rc = launch_gemm_fwd(p, h->G, mw_in, s);
+    int rc = launch_gemm_fwd(p, h->G, mw_in, s, hb_wait_epoch(h, mw_in));
     if (rc) return rc;
+    if (h->peer) {
+        const int Cc = (int)h->C;
+        rc = launch_misfit_batched(p, 1, h->n_total, h->d, fix, h->dobs_c, h->r, h->sums, s);
+        if (!rc) rc = peer_scalars(h->peer, h->sums, h->sums, Cc, 0, 1, nullptr, 0, s);  // sum d -> mean
+        if (!rc) rc = launch_misfit_batched(p, 2, h->n_total, h->d, fix, h->dobs_c, h->r, h->sums, s);
+        if (!rc) rc = launch_gemm_adj(p, h->G, h->r, nullptr, s);  // tiles land in their owners' staging blocks
+        // sum r^2 -- and the barrier of the reduce-scatter: a rank's flag follows its contraction
+        if (!rc) rc = peer_scalars(h->peer, h->sums, h->sums, Cc, 1, 1, nullptr, 0, s);
+        h->peer->nvlink_bytes += (int64_t)sizeof(double) * h->C * (h->cfg.ld - (h->pl.map.col[h->pl.map.me + 1] - h->pl.map.col[h->pl.map.me]));
+        h->launches += 6;
+        h->peer_steps += 1;
+        return rc;
+    }
     if (!h->hook) {
         rc = launch_misfit_batched(p, 0, p->nrows, h->d, fix, h->dobs_c, h->r, h->sums, s);
         if (!rc) rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
@@ -1112,6 +1291,90 @@ extern "C" int gi_hmcb_set_shard(gi_hmcb *h, int64_t n_total, const double *dobs
     return GI_OK;
 }
 
+// ---- peer mode set-up ------------------------------------------------------------------------------
+static void peer_columns(int64_t ld, int world, int64_t *col) {
+    const int64_t nstrips = ceil_div(ld, (int64_t)kAdjCols);
+    for (int q = 0; q <= world; ++q) col[q] = std::min<int64_t>(ld, kAdjCols * ((q * nstrips) / world));
+    col[world] = ld;
+}
+
+static int64_t peer_pitch(int64_t ld, int world) {
+    int64_t col[kPeerMax + 1], w = 0;
+    peer_columns(ld, world, col);
+    for (int q = 0; q < world; ++q) w = std::max(w, col[q + 1] - col[q]);
+    return std::max<int64_t>(w, 4);
+}
+
+extern "C" int64_t gi_hmcb_peer_bytes(const gi_hmcb *h, int32_t world) {
+    if (!h || world < 1 || world > kPeerMax) return -1;
+    const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
+    const int64_t ldp = peer_pitch(h->cfg.ld, world);
+    return kPeerCtlBytes + (int64_t)sizeof(double) * h->C * (world * ldp + (logc ? 4 : 2) * h->cfg.ld);
+}
+
+extern "C" int gi_hmcb_owned_columns(const gi_hmcb *h, int64_t *lo, int64_t *hi) {
+    GI_REQUIRE(h && lo && hi, "gi_hmcb_owned_columns: null pointer");
+    *lo = h->peer ? h->pl.map.col[h->pl.map.me] : 0;
+    *hi = h->peer ? std::min<int64_t>(h->pl.map.col[h->pl.map.me + 1], h->cfg.M) : h->cfg.M;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_set_peer(gi_hmcb *h, gi_peer *peer, int64_t n_total, const double *dobs_c_host) {
+    GI_REQUIRE(h && peer && dobs_c_host, "gi_hmcb_set_peer: null pointer");
+    GI_REQUIRE(!h->hook && !h->peer, "gi_hmcb_set_peer: the handle already has an exchange path");
+    GI_REQUIRE(peer->connected, "gi_hmcb_set_peer: call gi_peer_connect first");
+    GI_REQUIRE(n_total >= h->cfg.N, "gi_hmcb_set_peer: n_total is the GLOBAL observation count");
+    GI_REQUIRE(peer->bytes >= gi_hmcb_peer_bytes(h, peer->world),
+               "gi_hmcb_set_peer: the symmetric buffer is smaller than gi_hmcb_peer_bytes()");
+    const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;
+    const int64_t ld = h->cfg.ld, C = h->C;
+    const int P = peer->world, me = peer->rank;
+    cudaStream_t s = h->stream;
+    PeerLaunch &pl = h->pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.map.nranks = P;
+    pl.map.me = me;
+    peer_columns(ld, P, pl.map.col);
+    const int64_t ldp = peer_pitch(ld, P);
+    // symmetric layout: control block | staging [P][C][ldp] | xa [C][ld] | xb | (mwa | mwb)
+    const int64_t off_stage = kPeerCtlBytes;
+    const int64_t off_xa = off_stage + (int64_t)sizeof(double) * P * C * ldp;
+    const int64_t bx = (int64_t)sizeof(double) * C * ld;
+    for (int q = 0; q < P; ++q) pl.out.stage[q] = reinterpret_cast<double *>(peer->base[q] + off_stage);
+    pl.out.src_stride = C * ldp;
+    pl.out.ldp = ldp;
+    pl.stage_local = pl.out.stage[me];
+    pl.xflag = reinterpret_cast<const unsigned long long *>(peer->base[me] + kPeerFlagX);
+    // own slice first: the first k-chunk that starts inside it
+    pl.kc_rot = ceil_div(pl.map.col[me], h->plan->b_kchunk) % h->plan->b_nkc;
+    GI_CUDA(cudaMemsetAsync(peer->base[me] + off_stage, 0, (size_t)(peer->bytes - off_stage), s));
+    GI_CUDA(cudaMalloc(&h->sums_part, sizeof(double) * 8 * C));
+    GI_CUDA(cudaMemsetAsync(h->sums_part, 0, sizeof(double) * 8 * C, s));
+    GI_CUDA(cudaMalloc(&h->xepoch_src, sizeof(unsigned long long) * 8));
+    GI_CUDA(cudaMemsetAsync(h->xepoch_src, 0, sizeof(unsigned long long) * 8, s));
+    GI_CUDA(cudaStreamCreateWithFlags(&h->push_stream, cudaStreamNonBlocking));
+    GI_CUDA(cudaEventCreateWithFlags(&h->ev_upd, cudaEventDisableTiming));
+    GI_CUDA(cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming));
+    h->own_xa = h->xa; h->own_xb = h->xb; h->own_mwa = h->mwa; h->own_mwb = h->mwb;
+    h->xa = reinterpret_cast<double *>(peer->base[me] + off_xa);
+    h->xb = reinterpret_cast<double *>(peer->base[me] + off_xa + bx);
+    if (logc) {
+        h->mwa = reinterpret_cast<double *>(peer->base[me] + off_xa + 2 * bx);
+        h->mwb = reinterpret_cast<double *>(peer->base[me] + off_xa + 3 * bx);
+    } else {
+        h->mwa = h->xa; h->mwb = h->xb;
+    }
+    GI_CUDA(cudaMemcpyAsync(h->dobs_c, dobs_c_host, sizeof(double) * h->cfg.N, cudaMemcpyHostToDevice, s));
+    GI_CUDA(cudaStreamSynchronize(s));
+    h->n_total = n_total;
+    h->peer = peer;
+    h->plan->b_peer = &h->pl;
+    h->wait_xa = h->wait_xb = 0;
+    h->push_pending = false;
+    h->has_state = false;
+    return GI_OK;
+}
+
 // one batched misfit_and_grad at (x_in, mw_in) + the fused update
 static int hb_grad_eval_and_update(gi_hmcb *h, const double *x_in, const double *mw_in, double *x_out,
                                    double *mw_out, double *grad_out, double dt, const int32_t *L_dev,
@@ -1119,11 +1382,14 @@ static int hb_grad_eval_and_update(gi_hmcb *h, const double *x_in, const double 
     gi_plan *p = h->plan;
     cudaStream_t s = h->stream;
     int rc = hb_data_pass(h, mw_in);
+    if (!rc) rc = hb_pre_update(h);
     if (rc) return rc;
-    rc = launch_update_batched(p, &h->cfg.reg, nullptr, h->hook ? h->g_ext : h->gdata, x_in, mw_in,
+    const double *gsrc = h->peer ? h->pl.stage_local : (h->hook ? h->g_ext : h->gdata);
+    rc = launch_update_batched(p, &h->cfg.reg, nullptr, gsrc, x_in, mw_in,
                                h->mwapr, h->wmsq, h->low, h->high, h->p, x_out, mw_out, grad_out, dt,
-                               L_dev, step, uniform_mode, h->sums, s);
+                               L_dev, step, uniform_mode, h->peer ? h->sums_part : h->sums, s);
     h->launches += 1;
+    if (!rc) rc = hb_post_update(h);
     return rc;
 }
 
@@ -1221,21 +1487,27 @@ static int hb_run(gi_hmcb *h, int32_t Lmax, double dt, const int32_t *L_dev, gi_
     };
     int rc = trace(0, h->x_cur);
     // opening half step from the cached gradients (hmc.py:104-118); K0 -> sums[c][5]
+    if (!rc) rc = hb_pre_update(h);
     if (!rc)
         rc = launch_update_batched(p, &h->cfg.reg, h->g_cur, nullptr, h->x_cur, h->mw_cur, h->mwapr,
                                    h->wmsq, h->low, h->high, h->p, h->xa, h->mwa, nullptr, dt, L_dev,
-                                   0, 3, h->sums, s);
+                                   0, 3, h->peer ? h->sums_part : h->sums, s);
     h->launches += 1;
+    if (!rc) rc = hb_post_update(h);
+    if (!rc) rc = hb_push(h, h->xa, h->mwa);
     double *xin = h->xa, *xout = h->xb, *mwin = h->mwa, *mwout = h->mwb;
     for (int i = 1; i <= Lmax && !rc; ++i) {
         rc = hb_grad_eval_and_update(h, xin, mwin, xout, mwout, h->gnew, dt, L_dev, i,
                                      metropolis ? 0 : 0);
+        if (!rc) rc = hb_push(h, xout, mwout);
         if (!rc) rc = trace(i, xin);
         double *tp = xin; xin = xout; xout = tp;
         if (logc) { tp = mwin; mwin = mwout; mwout = tp; }
         else { mwin = xin; mwout = xout; }
     }
     delete[] hs;
+    // peer mode: the positions the commit copies were completed by the last push
+    if (!rc && h->peer) rc = peer_wait_x(h->peer, h->pl.map, hb_wait_epoch(h, xin), s);
     if (rc || !metropolis) return rc;
     metropolis_batched_kernel<<<1, 64, 0, s>>>(h->st, h->sums, alpha, L_dev, (int)C, 0);
     GI_LAUNCH_CHECK();
@@ -1416,7 +1688,7 @@ static int launch_update_modes(gi_hmcb *h, const double *grad_in, const double *
     a.x_in = x_in; a.mw_in = mw_in; a.mwapr = h->mwapr; a.wmsq = h->wmsq; a.low = h->low;
     a.high = h->high; a.p = h->p; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;
     a.dt = h->stream_dt; a.M = p->M; a.ld = p->ld; a.reg = h->cfg.reg;
-    a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = h->sums;
+    a.blockpart = p->b_blockpart; a.counter = p->b_counter; a.sums = h->peer ? h->sums_part : h->sums;
     if (gdata) { a.gp_ldk = p->b_gp_ldk; a.gp_piece_stride = p->b_gp_piece_stride; }
     BatchCtl ctl;
     memset(&ctl, 0, sizeof(ctl));
@@ -1427,7 +1699,9 @@ static int launch_update_modes(gi_hmcb *h, const double *grad_in, const double *
         ctl.qp = h->qp;
         ctl.qp_slot_stride = (int64_t)h->C * p->ld;
     }
-    dim3 grid((unsigned)p->upd_blocks, (unsigned)p->b_C);
+    const int64_t blocks = peer_slice(p, a, gdata != nullptr);
+    if (blocks == 0) return GI_OK;
+    dim3 grid((unsigned)blocks, (unsigned)p->b_C);
     update_batched_kernel<<<grid, kUpdThreads, 0, h->stream>>>(a, ctl);
     GI_LAUNCH_CHECK();
     return GI_OK;
@@ -1488,10 +1762,13 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         int rc = GI_OK;
         if (any_active) {
             rc = hb_data_pass(h, h->s_mwin);
+            if (!rc) rc = hb_pre_update(h);
             if (!rc)
-                rc = launch_update_modes(h, nullptr, h->hook ? h->g_ext : h->gdata, h->s_xin,
+                rc = launch_update_modes(h, nullptr,
+                                         h->peer ? h->pl.stage_local : (h->hook ? h->g_ext : h->gdata), h->s_xin,
                                          h->s_mwin, h->s_xout, h->s_mwout, h->gnew, modeA, nullptr);
             h->launches += 1;
+            if (!rc) rc = hb_post_update(h);
             if (rc) return rc;
         }
         if (any_fin || any_start) {
@@ -1531,11 +1808,18 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         }
         if (any_start) {
             // opening half step of the next trajectory from the (possibly just committed) state
-            rc = launch_update_modes(h, h->g_cur, nullptr, h->x_cur, h->mw_cur, h->s_xout, h->s_mwout,
-                                     nullptr, modeB, slotB);
+            rc = hb_pre_update(h);
+            if (!rc)
+                rc = launch_update_modes(h, h->g_cur, nullptr, h->x_cur, h->mw_cur, h->s_xout, h->s_mwout,
+                                         nullptr, modeB, slotB);
+            if (!rc) rc = hb_post_update(h);
             if (rc) return rc;
             h->launches += 1;
         }
+        // peer mode: every rank's slice of the new positions goes to the other ranks (hidden under
+        // the next step's forward pass)
+        rc = hb_push(h, h->s_xout, h->s_mwout);
+        if (rc) return rc;
         for (int c = 0; c < h->nchains; ++c) {
             gi_hmcb::ChainQ &q = h->cq[c];
             if (modeA[c] == 0) q.pos += 1;

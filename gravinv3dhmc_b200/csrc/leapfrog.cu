@@ -396,6 +396,8 @@ static int launch_update(gi_plan *p, const gi_reg_params *reg, const double *gra
     a.p_in = nullptr;
     a.gp_ldk = 0;
     a.gp_piece_stride = 0;
+    a.col0 = a.col1 = 0;
+    a.gp_nsrc = a.gp_src_stride = a.gp_pitch = 0;
     a.grad_in = grad_in; a.gpart = gpart; a.gparts = gparts;
     a.x_in = x_in; a.mw_in = mw_in; a.mwapr = mwapr; a.wmsq = wmsq; a.low = low; a.high = high;
     a.p = pm; a.x_out = x_out; a.mw_out = mw_out; a.grad_out = grad_out;

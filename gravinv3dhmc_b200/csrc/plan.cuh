@@ -4,6 +4,8 @@
 
 #include "common.cuh"
 
+namespace gi { struct PeerLaunch; }
+
 struct gi_plan {
     int64_t nrows, M, ld;
     int32_t nchains;
@@ -24,6 +26,7 @@ struct gi_plan {
     double *b_scratch_sums;   // [b_C][8]
     unsigned int *b_counter;  // [b_C]
     int64_t b_gp_ldk, b_gp_piece_stride;  // piece-major adjoint output (0 = plain [b_C][ld])
+    gi::PeerLaunch *b_peer;   // peer-memory exchange of a row-sharded batch (peer.cuh), or nullptr
 };
 
 
@@ -56,13 +59,21 @@ struct UpdateArgs {
     // piece): element j of a chain lives at gpart[(j / gp_ldk) * gp_piece_stride + j % gp_ldk];
     // gp_ldk == 0 means the plain [ld] layout
     int64_t gp_ldk, gp_piece_stride;
+    // peer mode (row-sharded batch, peer.cuh): this launch updates the columns [col0, col1) only
+    // (col1 == 0: all of them) and the data gradient is the sum of gp_nsrc staged partials, one per
+    // source rank, each a [chains][gp_pitch] block (stride gp_src_stride) whose column 0 is matrix column col0:
+    // gpart[k * gp_src_stride + (j - col0)] (the chain offset is already in gpart)
+    int64_t col0, col1;
+    int64_t gp_nsrc, gp_src_stride, gp_pitch;
 };
 
 int check_reg(const gi_reg_params *reg, int64_t M);
 // batched.cu
 int batched_plan_init(gi_plan *p);
 void batched_plan_free(gi_plan *p);
-int launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s);
+// wait_epoch != 0 (peer mode): X is being completed by the peers' pushes of that epoch
+int launch_gemm_fwd(gi_plan *p, const double *G, const double *X, cudaStream_t s,
+                    unsigned long long wait_epoch = 0);
 int launch_gemm_adj(gi_plan *p, const double *G, const double *R, double *out, cudaStream_t s,
                     int piece = 0, int npieces = 1);
 int launch_misfit_batched(gi_plan *p, int mode, int64_t n_total, double *d, const double *fix,
@@ -89,10 +100,11 @@ __device__ __forceinline__ void update_body(const UpdateArgs &a, bool copy_x) {
     __shared__ bool is_last;
     double um_t = 0.0, k_after_t = 0.0, k_before_t = 0.0;
     const bool mandatory = a.reg.constraint == GI_CONSTRAINT_MANDATORY;
+    const int64_t jend = a.col1 ? min(a.col1, a.M) : a.M;
     for (int v = 0; v < kUpdVec; ++v) {
-        const int64_t j0 = ((int64_t)blockIdx.x * kUpdVec + v) * (kUpdThreads * 4) + threadIdx.x * 4;
-        if (j0 >= a.M) continue;
-        const int nvalid = (int)min((int64_t)4, a.M - j0);
+        const int64_t j0 = a.col0 + ((int64_t)blockIdx.x * kUpdVec + v) * (kUpdThreads * 4) + threadIdx.x * 4;
+        if (j0 >= jend) continue;
+        const int nvalid = (int)min((int64_t)4, jend - j0);
         double grad[4], mwv[4], pv[4], xin[4];
         ldg4(a.mw_in + j0, mwv[0], mwv[1], mwv[2], mwv[3]);
         {
@@ -103,7 +115,13 @@ __device__ __forceinline__ void update_body(const UpdateArgs &a, bool copy_x) {
             ldg4(a.grad_in + j0, grad[0], grad[1], grad[2], grad[3]);
         } else {
             double gd[4] = {0.0, 0.0, 0.0, 0.0};
-            if (a.gp_ldk) {
+            if (a.gp_nsrc) {
+                for (int64_t k = 0; k < a.gp_nsrc; ++k) {  // rank order: the same bits whoever owns the slice
+                    double t0, t1, t2, t3;
+                    ldg_stream4(a.gpart + k * a.gp_src_stride + (j0 - a.col0), t0, t1, t2, t3);
+                    gd[0] += t0; gd[1] += t1; gd[2] += t2; gd[3] += t3;
+                }
+            } else if (a.gp_ldk) {
                 const int64_t pc = j0 / a.gp_ldk;  // groups of 4 never straddle a piece
                 ldg_stream4(a.gpart + pc * a.gp_piece_stride + (j0 - pc * a.gp_ldk), gd[0], gd[1], gd[2],
                             gd[3]);

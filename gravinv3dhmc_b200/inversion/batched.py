@@ -408,16 +408,20 @@ class HMCBatch:
         self.x = np.ascontiguousarray(np.tile(x0, (self.nchains, 1)))
         self.reg = reg_params(regularization, constraint, model.mshape, RegulFactor, beta, log_factor)
         sharded = getattr(model, "world", 1) > 1
-        # row-sharded batches: "device" = the C loop with all-reduce hooks (overlapped, streaming
-        # capable); "host" = the same exchange driven kernel by kernel from Python (_engine.py)
-        # ("device-hooks" forces the hook machinery on an unsharded model: reductions over one rank)
+        # row-sharded batches: "device" = the C loop, exchanging through peer memory over NVLink
+        # (csrc/peer.cu; GI_SHARD_EXCHANGE=nccl or driver="device-nccl": NCCL all-reduce hooks instead);
+        # "host" = the all-reduce exchange driven kernel by kernel from Python (_engine.py).
+        # "device-hooks" / "device-peer" force the hook / peer machinery on an unsharded model (one
+        # rank is its own peer), so that single-GPU test runs exercise them
         if driver == "auto":
             driver = "device" if getattr(model.Aw_pad, "is_cuda", False) else "host"
         self._npieces = None
         if isinstance(driver, tuple):
             driver, self._npieces = driver
+        self._peer, self.exchange = None, "none"
         if sharded and driver == "host":
             self._sh = _ShardedBatchState(self)
+            self.exchange = "nccl"
             return
         L = _lib.lib()
         m = model
@@ -434,9 +438,32 @@ class HMCBatch:
                                     _lib.ptr(self._host["apr"]), _lib.ptr(self._host["wmsq"]),
                                     _lib.stream_ptr(), C.byref(h)), "gi_hmcb_create")
         self._h = h
-        if sharded or driver == "device-hooks":
+        self._peer = None
+        from . import peer as _peer
+
+        if driver == "device-peer" or (sharded and driver == "device" and _peer.exchange_mode(m) == "peer"):
+            self._attach_peer(lo, hi)
+        elif sharded or driver in ("device-hooks", "device-nccl"):
             self._attach_shard_hooks(lo, hi)
+        self.exchange = "peer" if self._peer is not None else ("nccl" if sharded else "none")
         _lib.check(L.gi_hmcb_set_state(self._h, _lib.ptr(self.x)), "gi_hmcb_set_state")
+
+    def _attach_peer(self, lo, hi):
+        """row-sharded model on one NVLink node: the ranks map each other's memory and the kernels move
+        the data themselves (include/gravinv_b200.h: gi_hmcb_set_peer)"""
+        from .peer import PeerBuffer
+
+        m, L = self.model, _lib.lib()
+        world, rank = getattr(m, "world", 1), getattr(m, "rank", 0)
+        nbytes = int(L.gi_hmcb_peer_bytes(self._h, world))
+        self._peer = PeerBuffer(nbytes, rank, world, m.group if world > 1 else None)
+        dobs_c = np.ascontiguousarray(m.dobs[lo:hi] - float(np.mean(m.dobs)))
+        _lib.check(L.gi_hmcb_set_peer(self._h, self._peer.h, m.n_total, _lib.ptr(dobs_c)), "gi_hmcb_set_peer")
+        if world > 1:
+            import torch.distributed as dist
+
+            _lib.sync()
+            dist.barrier(group=m.group)  # every rank's buffers are zeroed and in place before the first store
 
     def _attach_shard_hooks(self, lo, hi):
         """row-sharded model: the device loop calls back here at its exchange points and
@@ -496,6 +523,9 @@ class HMCBatch:
         if self._h is not None:
             _lib.lib().gi_hmcb_destroy(self._h)
             self._h = None
+        if getattr(self, "_peer", None) is not None:
+            self._peer.close()
+            self._peer = None
 
     def __del__(self):
         try:

@@ -350,6 +350,39 @@ typedef int (*gi_shard_hook)(void *user, int32_t what, int32_t piece, int32_t as
 int gi_hmcb_set_shard(gi_hmcb *h, int64_t n_total, const double *dobs_c_host, double *gdata_dev,
                       int32_t npieces, double *red_dev, gi_shard_hook hook, void *user);
 
+/* Peer-memory exchange (the default of row-sharded batches on one NVLink / NVSwitch node): instead of
+ * calling back into a collective library at the exchange points, the ranks map each other's memory
+ * (CUDA IPC) and the kernels themselves move the data:
+ *   - the adjoint contraction's epilogue stores every 256-column tile into the staging block of the
+ *     rank that OWNS those columns (reduce-scatter fused into the contraction, transfer spread over
+ *     the whole pass); the owner's fused update sums the `world` staged partials in rank order and
+ *     updates only its own column slice (the replicated update of the hook path shrinks by `world`);
+ *   - the updated slice is pushed into every peer's position buffer by the copy engines (all-gather),
+ *     nearest reader first, and the next forward contraction starts at once on the own slice: its
+ *     CTAs poll a per-source-rank epoch flag before touching another rank's columns;
+ *   - per-chain scalars (sum d, sum r^2, Um, K) go through a slot table written by one small kernel
+ *     that adds the slots in rank order, so every rank holds identical bits (identical Metropolis
+ *     decisions) without any collective call.
+ * Protocol: every rank creates a gi_peer with the SAME byte count (>= gi_hmcb_peer_bytes), exchanges
+ * the 64-byte handles of gi_peer_export by any host-side means, calls gi_peer_connect with all of them
+ * ([world][64], own entry ignored), then gi_hmcb_set_peer; a host barrier must separate set_peer from
+ * the first sampler call.  All ranks must issue the same sequence of sampler calls with identical
+ * draws.  After set_peer the gradient the handle keeps (gi_hmcb_get_misfit's grad_host) is valid on
+ * the owned columns only (gi_hmcb_owned_columns). */
+typedef struct gi_peer gi_peer;
+int gi_peer_create(int32_t rank, int32_t world, int64_t bytes, gi_peer **out);
+int gi_peer_export(gi_peer *p, void *handle64);
+int gi_peer_connect(gi_peer *p, const void *handles);
+int gi_peer_destroy(gi_peer *p);
+/* bytes this rank has stored into its peers' memory so far (NVLink traffic accounting) */
+int64_t gi_peer_bytes_sent(const gi_peer *p);
+/* in-place sum over the ranks of n doubles (8..512, a multiple of 8) on the device, identical bits on
+ * every rank: the scalar exchange above, exposed for set-up reductions and tests */
+int gi_peer_allreduce_small(gi_peer *p, double *vec_dev, int32_t n, void *stream);
+int64_t gi_hmcb_peer_bytes(const gi_hmcb *h, int32_t world);
+int gi_hmcb_set_peer(gi_hmcb *h, gi_peer *peer, int64_t n_total, const double *dobs_c_host);
+int gi_hmcb_owned_columns(const gi_hmcb *h, int64_t *lo, int64_t *hi);
+
 /* Streaming mode: every chain runs its own sequence of proposals back to back.  All chains share
  * each gradient evaluation (one "batch step"), and a chain that ends a trajectory -- Metropolis test,
  * commit -- opens its next one inside the same step, so no chain idles while others finish longer

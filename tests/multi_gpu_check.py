@@ -65,12 +65,13 @@ def main():
     nch, nprops = 5, 5
     nacc = nrej = 0
     finals = {}
-    for driver in ("device", "host"):
+    for driver in ("device", "device-nccl", "host"):  # peer memory (default), NCCL hooks, host-driven
         bt = batched.HMCBatch(model, nch, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
                               "mandatory", 1000, dobs, 0.05, "MS", 0.001, 3, 0.05,
                               save_folder=os.path.join(tmp, "b%s%d_" % (driver, rank)), quiet=True,
                               driver=driver)
-        assert (bt._sh is None) == (driver == "device")
+        assert (bt._sh is None) == (driver != "host")
+        assert bt.exchange == {"device": "peer", "device-nccl": "nccl", "host": "nccl"}[driver]
         traces = []
         for _ in range(nprops):
             tr = {}
@@ -92,25 +93,90 @@ def main():
                 nacc += bool(t["accept"])
                 nrej += not t["accept"]
         finals[driver] = bt.x.copy()
-        if driver == "device":
+        if driver != "host":
             # the replicated state is bitwise identical on every rank
             xs = [torch.zeros(nch, M, dtype=torch.float64, device="cuda") for _ in range(world)]
             dist.all_gather(xs, torch.as_tensor(bt.x).cuda())
             assert all(torch.equal(xs[0], x) for x in xs)
             bt.close()
     assert np.allclose(finals["device"], finals["host"], rtol=1e-9, atol=0)
-    assert nacc > 0 and nrej >= 0  # the commit path ran (both drivers)
+    assert np.allclose(finals["device-nccl"], finals["host"], rtol=1e-9, atol=0)
+    assert nacc > 0 and nrej >= 0  # the commit path ran (all drivers)
+    # ---- a batch with REAL rejections (large step: the golden 'reject' chain's parameters), both
+    #      device exchanges: the reject / commit-skip branch of the sharded batch path ----
+    for driver in ("device", "device-nccl"):
+        bt = batched.HMCBatch(model, 4, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b, "mandatory",
+                              1000, dobs, 1.0, "Damping", 0.001, 3, 1.0,
+                              save_folder=os.path.join(tmp, "rj%s%d_" % (driver, rank)), quiet=True, driver=driver)
+        for _ in range(12):
+            bt.propose()
+        rej = 0
+        for c in range(4):
+            ref = onp.hmc_sample(om, 10 ** 6, 0, 0.1, [4, 9], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
+                                 "mandatory", 1000, 1.0, "Damping", 0.001, 3, 1.0, myrank=c, max_proposals=12)
+            assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
+            assert np.max(np.abs(bt.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"]))
+            rej += sum(1 for _, a in ref["log"] if not a)
+        assert rej > 0
+        nrej += rej
+        bt.close()
     # ---- streaming sampler over the row-sharded kernel (device driver), TV on the full grid ----
-    bs = batched.HMCBatch(model, 6, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
-                          "mandatory", 1000, dobs, 0.05, "TV", 0.001, 3, 0.05,
-                          save_folder=os.path.join(tmp, "st%d_" % rank), quiet=True)
-    bs.stream(10 ** 6, 0, max_proposals=4, write=(rank == 0))
-    for c in range(6):
-        ref = onp.hmc_sample(om, 10 ** 6, 0, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
-                             "mandatory", 1000, 0.05, "TV", 0.001, 3, 0.05, myrank=c, max_proposals=4)
-        assert [(L, bool(a)) for L, a in bs.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
-        assert np.max(np.abs(bs.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"]))
-    bs.close()
+    for driver in ("device", "device-nccl"):
+        bs = batched.HMCBatch(model, 6, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
+                              "mandatory", 1000, dobs, 0.05, "TV", 0.001, 3, 0.05,
+                              save_folder=os.path.join(tmp, "st%s%d_" % (driver, rank)), quiet=True, driver=driver)
+        bs.stream(10 ** 6, 0, max_proposals=4, write=(rank == 0))
+        for c in range(6):
+            ref = onp.hmc_sample(om, 10 ** 6, 0, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b_tv,
+                                 "mandatory", 1000, 0.05, "TV", 0.001, 3, 0.05, myrank=c, max_proposals=4)
+            assert [(L, bool(a)) for L, a in bs.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]]
+            assert np.max(np.abs(bs.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"]))
+        bs.close()
+    # ---- a wider grid (12 x 10 x 8 = 960 voxels -> several 256-column strips per rank): the column
+    #      slices of the peer path really are spread over the ranks; lockstep (with rejections) and
+    #      streaming, Damping and TV, against the oracle on the oracle-assembled kernel ----
+    xs, ys = np.meshgrid(np.linspace(40, 1160, 8), np.linspace(30, 970, 6))
+    xo, yo, zo = xs.ravel(), ys.ravel(), np.full(xs.size, -2.0)
+    rng = np.random.RandomState(11)
+    wmesh = onp.OracleMesh((0, 1200, 0, 1000, 0, 800), (100, 100, 100))
+    wtab, _ = wmesh.active_bounds()
+    _, Aor = onp.prism_gz(xo, yo, zo, wtab)
+    Awo, wmo, _, _ = onp.sensitivity_weighting(Aor)
+    rho = np.zeros(wmesh.shape)
+    rho[2:5, 3:7, 4:9] = 0.2
+    wd = Aor @ rho.ravel() + 0.01 * rng.randn(xo.size)
+    wmodel = potential.GravMagModule(wd, (0, 1200, 0, 1000, 0, 800), (100, 100, 100), (xo, yo, zo),
+                                     verbose=False, shard=(rank, world), group=dist.group.WORLD)
+    wom = onp.OracleModel(Awo, wmo, wd, wmesh.shape)
+    Mw = wmodel.M
+    assert Mw == 960
+    bw = np.zeros((Mw, 2))
+    bw[:, 1] = 0.3
+    for reg, delta, Sigma, alpha in (("TV", 0.02, 0.05, 0.05), ("Damping", 0.25, 1.0, 1.0)):
+        bb = bw if reg == "TV" else np.c_[np.full(Mw, -5.0), np.full(Mw, 5.0)]
+        for mode in ("lockstep", "stream"):
+            bt = batched.HMCBatch(wmodel, 7, delta, [3, 8], np.ones(Mw) * 0.001, np.ones(Mw) * 0.001, bb,
+                                  "mandatory", 1000, wd, alpha, reg, 0.001, 3, Sigma,
+                                  save_folder=os.path.join(tmp, "w%s%s%d_" % (reg, mode, rank)), quiet=True)
+            assert bt.exchange == "peer"
+            if mode == "lockstep":
+                for _ in range(8):
+                    bt.propose()
+            else:
+                bt.stream(10 ** 6, 0, max_proposals=8, write=False)
+            for c in range(7):
+                ref = onp.hmc_sample(wom, 10 ** 6, 0, delta, [3, 8], np.ones(Mw) * 0.001, np.ones(Mw) * 0.001,
+                                     bb, "mandatory", 1000, alpha, reg, 0.001, 3, Sigma, myrank=c,
+                                     max_proposals=8)
+                assert [(L, bool(a)) for L, a in bt.proposals[c]] == [(L, bool(a)) for L, a in ref["log"]], \
+                    (reg, mode, c)
+                assert np.max(np.abs(bt.x[c] - ref["x"])) < 1e-9 * np.max(np.abs(ref["x"])), (reg, mode, c)
+                if reg == "Damping":
+                    nrej += sum(1 for _, a in ref["log"] if not a)
+            xs_all = [torch.zeros(7, Mw, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(xs_all, torch.as_tensor(bt.x).cuda())
+            assert all(torch.equal(xs_all[0], x) for x in xs_all)  # bitwise identical replicas
+            bt.close()
     # ---- row-sharded regularised CG and bootstrap (gi_cg_set_shard) against the oracle ----
     from gravinv3dhmc_b200.inversion import reginv
 
