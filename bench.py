@@ -63,11 +63,20 @@ FP64_PEAK_TFLOPS = 37.1
 FP64_PEAK_SRC = "measured here (tools/probes/fp64_peak.cu: DMMA m8n8k4 = DFMA = 37.1 TFLOP/s FP64)"
 
 
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full`
-# capture of this command at N = 1 (profiles/r01_gemm_c5_ncu_full.txt); algorithmic bytes are
-# 8*N*M = 137.44 GB.  (The same capture's counters of the adjoint kernel overflowed; its traffic at
-# 1/8 of the rows, profiles/r01_gemm_c64_ncu_full_final.txt, is 17.33 GB = 1.009 x algorithmic.)
-NCU_TRAFFIC_BYTES = {("c5", 1, 64, "gemm_fwd"): 138.590020e9 + 0.124359e9}
+# DRAM traffic per launch of the dominant kernels (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture each): read from profiles/r02_traffic.json, which tools/ncu_summary.py
+# writes from the captured reports and which names the report and the metric for every entry.
+TRAFFIC_FILE = os.path.join("profiles", "r02_traffic.json")
+
+
+def measured_traffic(workload, world, nch, kernel):
+    p = os.path.join(ROOT, TRAFFIC_FILE)
+    if not os.path.exists(p):
+        return None, None
+    for e in json.load(open(p)).get("entries", []):
+        if (e["workload"], e["n_gpus"], e["chains"], e["kernel"]) == (workload, world, nch, kernel):
+            return float(e["dram_bytes"]), "%s: %s (%s)" % (TRAFFIC_FILE, e["metric"], e["source"])
+    return None, None
 
 
 def peaks():
@@ -184,6 +193,7 @@ def cpu_reference_arm(workload, sample_rows, steps, cores=None, warm=0):
     wall = time.perf_counter() - t0
     # every worker streams the sample (2 passes per gradient evaluation, steps+1 evaluations)
     rate_sample = sum(s / t for s, t in out)            # chain-steps/s on the row sample
+    chain_seconds = max(t for _, t in out)              # the timed steps of the slowest chain
     value = rate_sample * sample_rows / N               # scaled to the full observation count
     return dict(value=value, unit="leapfrog steps/s", cores=cores, kind="port",
                 sample=("%d of %d observation rows x %d voxels (%.2f GB Aw), %d independent "
@@ -191,13 +201,51 @@ def cpu_reference_arm(workload, sample_rows, steps, cores=None, warm=0):
                         "inversion/hmc.py:_leapfrog + potential.py:misfit_and_grad, numpy dgemv); "
                         "rate scaled by rows/N" % (sample_rows, N, tab.shape[0], A.nbytes / 1e9,
                                                   cores, steps)),
-                assembly_mpairs_per_s=A.size / t_asm / 1e6, wall_s=wall,
+                assembly_mpairs_per_s=A.size / t_asm / 1e6, wall_s=wall, chain_seconds=chain_seconds,
                 gbytes_per_s=rate_sample * 2 * A.nbytes / 1e9)
 
 
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def selfcheck_assembly(model, obs, rank, world, dev, group):
+    """bench-scale parity, part 1: sampled rows of the device-assembled, weighted kernel against the
+    CPU oracle's closed-form prism kernel (oracle/csrc/oracle_prism.c == gravmag/_prism.pyx:263-290,
+    checker only), and unit column norms of Aw over ALL rows (inversion/potential.py:232-264)."""
+    import torch
+    import torch.distributed as dist
+
+    from gravinv3dhmc_b200 import _lib
+    from oracle import oracle_np as onp
+
+    onp.build()
+    lo, hi = model.rows
+    n = hi - lo
+    # first / last rows of the shard, its middle, and the two rows around element index 2^32
+    cand = [0, 1, n // 2 - 1, n // 2, n - 2, n - 1]
+    edge = (1 << 32) // model.ld
+    cand += [edge - 1 - lo, edge - lo] if lo <= edge - 1 and edge < hi else []
+    rows = sorted({r for r in cand if 0 <= r < n})
+    g = np.array(rows) + lo
+    tab = model.mesh.bounds_table()
+    _, A = onp.prism_gz(obs[0][g], obs[1][g], obs[2][g], tab, threads=min(len(rows), os.cpu_count() or 1))
+    A = torch.as_tensor(A, device=dev)
+    got = model.Aw_pad[rows, : model.M] * model.wm_dev[: model.M]  # Aw = A WmInv  ->  A = Aw Wm
+    err_rows = _rel(got, A)
+    # every column of Aw has unit L2 norm (KA3): one more pass over the whole kernel
+    ss = torch.zeros(model.ld, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().gi_colsumsq(_lib.ptr(model.Aw_pad), n, model.M, model.ld, _lib.ptr(ss), 0,
+                                      _lib.stream_ptr()), "gi_colsumsq")
+    if world > 1:
+        dist.all_reduce(ss, group=group)
+    err_norm = float((ss[: model.M] - 1.0).abs().max())
+    return {"aw_rows_vs_oracle": err_rows, "rows_checked": [int(v) for v in g], "aw_column_norms": err_norm}
+
+
 def gpu_arm(args):
     if os.environ.get("GI_BENCH_WATCHDOG"):  # diagnostics: dump all stacks and exit if the run hangs
         import faulthandler
@@ -230,7 +278,14 @@ def gpu_arm(args):
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    # ---- workload: the named one, or -- if this rank's shard plus ~8 GB of chain state does not fit
+    def rmax(v):  # max over ranks of a host scalar
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t[0])
+
+    # ---- workload: the named one, or -- if this rank's shard plus the chain state does not fit
     # the free HBM -- the next smaller rung (said in config.workload; every rank decides alike) ----
     free, total = torch.cuda.mem_get_info()
     ladder = [args.workload] + [w for w in ("c5_half", "c5_quarter", "mid") if w != args.workload]
@@ -239,7 +294,7 @@ def gpu_arm(args):
         (nz, ny, nx), _, side = WORKLOADS[wl]
         N, M = side * side, nz * ny * nx
         lo, hi = potential.split_rows(N, world)[rank]
-        need = (hi - lo) * _lib.padded_ld(M) * 8 + 26 * _lib.padded_ld(M) * 8 * max(args.chains, 8)
+        need = (hi - lo) * _lib.padded_ld(M) * 8 + 30 * _lib.padded_ld(M) * 8 * max(args.chains, 8)
         fits = torch.tensor([1.0 if need < free - (2 << 30) else 0.0], device=dev)
         if world > 1:
             dist.all_reduce(fits, op=dist.ReduceOp.MIN, group=group)
@@ -252,17 +307,14 @@ def gpu_arm(args):
         fallback_note = " [%s did not fit the %.0f GB free HBM, ran %s]" % (args.workload, free / 1e9, wl)
         args.workload = wl
     mrange, mspacing, obs, rho = workload_geometry(args.workload)
-    e0, e1 = ev(), ev()
-    torch.cuda.synchronize()
-    e0.record()
     model = potential.GravMagModule(np.zeros(N), mrange, mspacing, obs, coordinate="cartesian",
                                     shard=(rank, world) if world > 1 else None, group=group,
                                     verbose=False, timing=True)
-    e1.record()
     torch.cuda.synchronize()
     t_asm = model.timing["assemble_ms"] * 1e-3
     t_wgt = model.timing["weight_ms"] * 1e-3
     n_local = hi - lo
+    selfcheck = {} if args.no_selfcheck else selfcheck_assembly(model, obs, rank, world, dev, group)
     # synthetic observations: dobs = A rho_true + 2% noise
     wm = model.Wm.diagonal()
     d_local = model.forward_local(wm * rho)
@@ -289,11 +341,89 @@ def gpu_arm(args):
     p0 = torch.zeros(model.ld, dtype=torch.float64, device=dev)
     p0[:M] = torch.as_tensor(rs.randn(M) * HMC["Sigma"], device=dev)
     x0 = chain.initial_model
+    eng = model.engine()
+    s = _lib.stream_ptr()
+    hbm_peak, hbm_src = peaks()
+    bytes_pass = 8.0 * n_local * M  # algorithmic: every element of the shard once per pass
 
-    launches = 0
+    def time_kernel(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b_ = ev(), ev()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) * 1e-3 / reps
+
+    reps = max(3, min(args.steps, 10))
+
+    # ---- single chain (C = 1): the two HBM-bound GEMV passes and the single-pass evaluation, timed
+    # alone, and the device-resident leapfrog rate (north_star: >= 70 % of HBM on these passes) ----
+    def c1_block():
+        xv = eng.vec(x0)
+        t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemv_fwd(eng.plan, _lib.ptr(eng.Aw), _lib.ptr(xv),
+                                                               _lib.ptr(eng.d), s)), reps)
+        t_adj = time_kernel(lambda: _lib.check(lib.gi_gemv_adj(eng.plan, _lib.ptr(eng.Aw),
+                                                               _lib.ptr(eng.r), _lib.ptr(eng.g), s)), reps)
+        out = {"gemv_fwd": {"ms": t_fwd * 1e3, "dram_GBps": bytes_pass / t_fwd / 1e9,
+                            "frac_of_hbm_peak": bytes_pass / t_fwd / 1e9 / hbm_peak},
+               "gemv_adj": {"ms": t_adj * 1e3, "dram_GBps": bytes_pass / t_adj / 1e9,
+                            "frac_of_hbm_peak": bytes_pass / t_adj / 1e9 / hbm_peak}}
+        fh = C.c_void_p()
+        if os.environ.get("GI_FUSED_GEMV", "") != "0" and \
+                lib.gi_fused_create(n_local, M, _lib.padded_ld(M), _lib.ptr(eng.Aw), s, C.byref(fh)) == 0:
+            gtmp = eng.vec()
+            t_fu = time_kernel(lambda: _lib.check(lib.gi_fused_pass(
+                fh, _lib.ptr(xv), _lib.ptr(eng.dobs_c), None, 1, _lib.ptr(eng.d), _lib.ptr(gtmp), s)), reps)
+            lib.gi_fused_destroy(fh)
+            # ONE pass over Aw yields both products: DRAM bytes 8 N M, algorithmic bytes 2 x 8 N M
+            out["fused_pass"] = {"ms": t_fu * 1e3, "dram_GBps": bytes_pass / t_fu / 1e9,
+                                 "frac_of_hbm_peak": bytes_pass / t_fu / 1e9 / hbm_peak,
+                                 "algorithmic_GBps": 2 * bytes_pass / t_fu / 1e9}
+        out["bytes_per_pass"] = bytes_pass
+        out["hbm_peak_GBps"] = hbm_peak
+        return out
+
+    def c1_rate(run_steps_c1, k=20):
+        run_steps_c1(3)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=group)
+        a, b_ = ev(), ev()
+        a.record()
+        run_steps_c1(k)
+        b_.record()
+        torch.cuda.synchronize()
+        ms_ = rmax(a.elapsed_time(b_))
+        return {"steps_per_s": k / (ms_ * 1e-3), "ms_per_step": ms_ / k, "steps": k,
+                "algorithmic_GBps": 2 * 8.0 * N * M * k / (ms_ * 1e-3) / 1e9}
+
+    def c1_runner():
+        if world == 1:
+            chain._ensure_handle(alpha)
+            chain._sync_state(x0)
+            return (lambda k: _lib.check(lib.gi_hmc_leapfrog_steps(chain._h, _lib.ptr(p0), int(k), float(dt)),
+                                         "gi_hmc_leapfrog_steps")), (lambda: int(lib.gi_hmc_launch_count(chain._h)))
+        reg = reg_params(HMC["regularization"], "mandatory", model.mshape, alpha, HMC["beta"], 1000)
+        st = sharded._ShardState(chain, alpha)
+        sharded._set_state(st, chain, reg, x0)
+
+        def run(k):
+            st.p.copy_(p0)
+            xin, outs = st.x_cur, (st.xa, st.xb)
+            for i in range(k):  # k gradient evaluations + fused updates (hmc.py:117-152)
+                xout = outs[i & 1]
+                sharded._grad_eval(st, chain, reg, xin, xin, xout, xout, None, dt, dt, 1)
+                xin = xout
+
+        return run, (lambda: int(st.eng.launches))
+
     nch = args.chains
     bt = None
-    # ---- the timed region: K leapfrog steps of every chain, everything resident in HBM ----
+    c1 = None
     if nch > 1:
         from gravinv3dhmc_b200.inversion import batched
         bt = batched.HMCBatch(model, nch, HMC["delta"], HMC["Lrange"], np.full(M, HMC["init"]),
@@ -313,94 +443,84 @@ def gpu_arm(args):
 
         def launch_count():
             return int(lib.gi_hmcb_launch_count(bt._h))
-    elif world == 1:
-        chain._ensure_handle(alpha)
-        chain._sync_state(x0)
-
-        def run_steps(k):
-            _lib.check(lib.gi_hmc_leapfrog_steps(chain._h, _lib.ptr(p0), int(k), float(dt)),
-                       "gi_hmc_leapfrog_steps")
-
-        def launch_count():
-            return int(lib.gi_hmc_launch_count(chain._h))
     else:
-        reg = reg_params(HMC["regularization"], "mandatory", model.mshape, alpha, HMC["beta"], 1000)
-        st = sharded._ShardState(chain, alpha)
-        sharded._set_state(st, chain, reg, x0)
+        run_steps, launch_count = c1_runner()
 
-        def run_steps(k):
-            st.p.copy_(p0)
-            xin, outs = st.x_cur, (st.xa, st.xb)
-            # k gradient evaluations + fused updates (hmc.py:117-152)
-            for i in range(k):
-                xout = outs[i & 1]
-                sharded._grad_eval(st, chain, reg, xin, xin, xout, xout, None, dt, dt, 1)
-                xin = xout
-
-        def launch_count():
-            return int(st.eng.launches)
-
-    run_steps(args.warmup)
+    # ---- the timed region: leapfrog steps of every chain, everything resident in HBM.  K steps as
+    # asked, repeated so that the region lasts >= 2 s on every GPU count (the repetition count is
+    # derived from the warm-up's own timing, maximised over the ranks) ----
     torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    run_steps(args.warmup)
+    e1.record()
+    torch.cuda.synchronize()
+    est = rmax(e0.elapsed_time(e1)) * 1e-3 / args.warmup
+    nrep = max(1, int(np.ceil(args.min_seconds / max(est * args.steps, 1e-9))))
     if world > 1:
         dist.barrier(group=group)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = launch_count()
+    sent0 = bt._peer.bytes_sent() if bt is not None and bt._peer is not None else 0
     torch.cuda.synchronize()
     e0, e1 = ev(), ev()
     e0.record()
-    run_steps(args.steps)
+    for _ in range(nrep):
+        run_steps(args.steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier(group=group)
-    ms = e0.elapsed_time(e1)
+    ms = rmax(e0.elapsed_time(e1))
     launches = launch_count() - l0
+    timed_steps = nrep * args.steps
     clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        ms = float(t[0])
-    steps_per_s = nch * args.steps / (ms * 1e-3)  # chain-steps per second over the whole job
+    steps_per_s = nch * timed_steps / (ms * 1e-3)  # chain-steps per second over the whole job
+    exchange = None
+    if bt is not None and world > 1:
+        exchange = {"path": bt.exchange}
+        if bt._peer is not None:
+            sent = bt._peer.bytes_sent() - sent0
+            exchange.update(nvlink_bytes_per_step_per_gpu=sent / timed_steps,
+                            allreduce_equivalent_bytes=2.0 * (world - 1) / world * cp * model.ld * 8)
 
-    # ---- per-kernel roofline: the two big passes, timed alone with events ----
-    eng = model.engine()
-    s = _lib.stream_ptr()
-
-    def time_kernel(fn, reps):
-        for _ in range(2):
-            fn()
-        torch.cuda.synchronize()
-        a, b_ = ev(), ev()
-        a.record()
-        for _ in range(reps):
-            fn()
-        b_.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b_) * 1e-3 / reps
-
-    reps = max(3, min(args.steps, 10))
-    hbm_peak, hbm_src = peaks()
-    bytes_pass = 8.0 * n_local * M  # algorithmic: every element of the shard once per pass
+    # ---- per-kernel roofline: the two big passes, timed alone with events; and bench-scale parity,
+    # part 2: the same launches' results on sampled rows / columns against a torch FP64 product ----
+    traffic, traffic_src = None, None
     if nch > 1:
         plan = C.c_void_p()
         _lib.check(lib.gi_plan_create(n_local, M, model.ld, nch, C.byref(plan)), "gi_plan_create")
         cpi, npad = C.c_int32(), C.c_int64()
         _lib.check(lib.gi_plan_batch_info(plan, C.byref(cpi), C.byref(npad)))
         f64 = dict(dtype=torch.float64, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7 + rank)
         Xb = torch.zeros((cpi.value, model.ld), **f64)
-        Xb[:nch, :M] = torch.as_tensor(x0, device=dev)
+        Xb[:nch, :M] = torch.rand((nch, M), generator=gen, **f64)
         Db = torch.zeros((cpi.value, n_local), **f64)
         Rb = torch.zeros((cpi.value, npad.value), **f64)
-        Rb[:nch, :n_local] = 1e-3
+        Rb[:nch, :n_local] = torch.randn((nch, n_local), generator=gen, **f64)
         Gb = torch.zeros((cpi.value, model.ld), **f64)
         t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemm_fwd(plan, _lib.ptr(eng.Aw), _lib.ptr(Xb),
                                                                _lib.ptr(Db), s)), reps)
         t_adj = time_kernel(lambda: _lib.check(lib.gi_gemm_adj(plan, _lib.ptr(eng.Aw), _lib.ptr(Rb),
                                                                _lib.ptr(Gb), s)), reps)
         lib.gi_plan_destroy(plan)
+        if not args.no_selfcheck:
+            edge = (1 << 32) // model.ld  # first row whose elements sit beyond index 2^32
+            rows = sorted({r for r in (0, 1, n_local // 3, edge - 1, edge, n_local - 2, n_local - 1)
+                           if 0 <= r < n_local})
+            ref = eng.Aw[rows, :M] @ Xb[:nch, :M].T
+            selfcheck["gemm_fwd_rows_vs_torch"] = _rel(Db[:nch, rows].T, ref)
+            cols = torch.unique(torch.cat([torch.linspace(0, M - 1, 56, device=dev).long(),
+                                           torch.tensor([0, 1, 255, 256, M - 257, M - 256, M - 2, M - 1],
+                                                        device=dev)]))
+            ref = Rb[:nch, :n_local] @ eng.Aw[:, cols]
+            selfcheck["gemm_adj_cols_vs_torch"] = _rel(Gb[:nch, cols], ref)
+            selfcheck["elements_beyond_2^32"] = bool(n_local * model.ld > (1 << 32))
+            del ref
         del Xb, Db, Rb, Gb
         flops_pass = 2.0 * n_local * M * nch  # algorithmic: one FMA per (row, voxel, chain)
         kern = {"gemm_fwd": {"ms": t_fwd * 1e3, "TFLOPs": flops_pass / t_fwd / 1e12,
@@ -410,33 +530,48 @@ def gpu_arm(args):
         dom = "gemm_adj" if t_adj >= t_fwd else "gemm_fwd"
         achieved, peak, unit, bound = kern[dom]["TFLOPs"], FP64_PEAK_TFLOPS, "TFLOP/s", "tensor"
         peak_src = FP64_PEAK_SRC
+        if not args.no_c1:
+            c1 = c1_block()
+            run_c1, _ = c1_runner()
+            c1["leapfrog"] = c1_rate(run_c1)
     else:
-        xv = eng.vec(x0)
-        t_fwd = time_kernel(lambda: _lib.check(lib.gi_gemv_fwd(eng.plan, _lib.ptr(eng.Aw), _lib.ptr(xv),
-                                                               _lib.ptr(eng.d), s)), reps)
-        t_adj = time_kernel(lambda: _lib.check(lib.gi_gemv_adj(eng.plan, _lib.ptr(eng.Aw),
-                                                               _lib.ptr(eng.r), _lib.ptr(eng.g), s)), reps)
-        kern = {"gemv_fwd": {"ms": t_fwd * 1e3, "GBps": bytes_pass / t_fwd / 1e9},
-                "gemv_adj": {"ms": t_adj * 1e3, "GBps": bytes_pass / t_adj / 1e9}}
-        dom = "gemv_adj" if t_adj >= t_fwd else "gemv_fwd"
+        c1 = c1_block()
+        kern = {k: {"ms": v["ms"], "GBps": v["dram_GBps"]} for k, v in c1.items() if isinstance(v, dict)}
+        dom = "fused_pass" if "fused_pass" in kern and world == 1 else \
+            ("gemv_adj" if kern["gemv_adj"]["ms"] >= kern["gemv_fwd"]["ms"] else "gemv_fwd")
         achieved, peak, unit, bound, peak_src = kern[dom]["GBps"], hbm_peak, "GB/s", "hbm", hbm_src
-        if world == 1 and os.environ.get("GI_FUSED_GEMV", "") != "0":
-            # the single-chain sampler evaluates d and Aw^T r in ONE pass over Aw (csrc/fused.cu): the
-            # dominant kernel of the step.  Algorithmic bytes stay 2 x 8 N M per evaluation (two
-            # products), its DRAM traffic is 8 N M -- so the algorithmic rate may exceed the HBM peak.
-            fh = C.c_void_p()
-            if lib.gi_fused_create(n_local, M, _lib.padded_ld(M), _lib.ptr(eng.Aw), s, C.byref(fh)) == 0:
-                gtmp = eng.vec()
-                t_fu = time_kernel(lambda: _lib.check(lib.gi_fused_pass(
-                    fh, _lib.ptr(xv), _lib.ptr(eng.dobs_c), None, 1, _lib.ptr(eng.d), _lib.ptr(gtmp), s)), reps)
-                lib.gi_fused_destroy(fh)
-                kern["fused_pass"] = {"ms": t_fu * 1e3, "GBps": 2 * bytes_pass / t_fu / 1e9,
-                                      "dram_GBps": bytes_pass / t_fu / 1e9}
-                dom, achieved = "fused_pass", kern["fused_pass"]["GBps"]
+    traffic, traffic_src = measured_traffic(args.workload, world, nch, dom)
     if world > 1:
         t = torch.tensor([achieved], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
         achieved = float(t[0])
+        if not args.no_selfcheck and bt is not None:
+            # the exchanged gradient of the sampler's start state on 64 owned columns against a
+            # rank-local recompute (torch FP64) summed over the ranks by NCCL
+            lo_c, hi_c = C.c_int64(), C.c_int64()
+            _lib.check(lib.gi_hmcb_owned_columns(bt._h, C.byref(lo_c), C.byref(hi_c)))
+            bounds = [None] * world
+            dist.all_gather_object(bounds, (int(lo_c.value), int(hi_c.value)), group=group)
+            gh = np.zeros((nch, M))  # the leapfrog runs above never commit: still the start state's gradient
+            _lib.check(lib.gi_hmcb_get_misfit(bt._h, None, None, None, _lib.ptr(gh)), "gi_hmcb_get_misfit")
+            xs = torch.as_tensor(x0, device=dev)
+            d_loc = eng.Aw[:, :M] @ xs
+            tot = d_loc.sum().reshape(1)
+            dist.all_reduce(tot, group=group)
+            r_loc = (d_loc - tot / N) - eng.dobs_c
+            # every rank contributes to every rank's columns: reduce the samples of all slices
+            allc = [torch.linspace(a_, b_ - 1, max(2, 64 // world), device=dev).long() if b_ > a_
+                    else torch.zeros(0, dtype=torch.long, device=dev) for a_, b_ in bounds]
+            part = torch.cat([r_loc @ eng.Aw[:, c_] for c_ in allc])
+            dist.all_reduce(part, group=group)
+            mine = allc[rank]
+            off = sum(len(c_) for c_ in allc[:rank])
+            apr = torch.as_tensor(chain.aprior_model, device=dev)
+            err = 0.0
+            if len(mine):
+                ref = 2.0 * part[off: off + len(mine)] + alpha * 2.0 * (xs[mine] - apr[mine])
+                err = _rel(torch.as_tensor(gh[0], device=dev)[mine], ref)
+            selfcheck["exchanged_gradient_vs_local_recompute"] = rmax(err)
 
     # ---- e2e: the public per-proposal call with host buffers (momentum in, state out) ----
     e2e = None
@@ -451,18 +586,15 @@ def gpu_arm(args):
             dist.barrier(group=group)
         t0 = time.perf_counter()
         # streaming sampler: chains restart inside the step they finish in (no idling); the draws are
-        # prepared on host threads while the GPU runs.  Measured over the steady-state window that
-        # ends when the first chain has completed its quota of proposals (after that the batch
-        # drains and chains run dry one by one).
-        nprop = max(5, int(round(args.steps / 12.5)) + 2)
+        # prepared on host threads while the GPU runs.  Two figures: the WHOLE run (pipeline fill and
+        # drain included) and the steady-state window that opens when the first proposal of the batch
+        # has finished and closes when the first chain has completed its quota.
+        nprop = max(args.e2e_proposals, int(round(args.steps / 12.5)) + 2)
         bt.advance_cap = 4  # records (and the window's clock) come back every <= 4 batch steps
         bt.proposals = [[] for _ in range(nch)]
         window = {}
 
         def on_record(c, r, acc):
-            # steady state: the window opens when the first proposal of the batch has finished (the
-            # pipeline of draws is filled, every chain is mid-trajectory) and closes when the first
-            # chain has completed its quota (after that the batch drains, chains run dry one by one)
             if "t0" not in window:
                 torch.cuda.synchronize()
                 window.update(t0=time.perf_counter(), s0=bt.stream_steps,
@@ -473,72 +605,68 @@ def gpu_arm(args):
                               props=sum(len(q) for q in bt.proposals) - window["p0"])
 
         bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
+        torch.cuda.synchronize()
+        t_whole = rmax(time.perf_counter() - t0)
+        props_whole = sum(len(q) for q in bt.proposals)
+        chain_steps_whole = sum(L for q in bt.proposals for L, _ in q)
         if window.get("steps", 0) <= 0:  # run too short for a steady-state window: use all of it
-            window.update(t=time.perf_counter() - t0, steps=bt.stream_steps,
-                          props=sum(len(q) for q in bt.proposals))
+            window.update(t=t_whole, steps=bt.stream_steps, props=props_whole)
         api = ("HMCBatch.stream -> gi_hmcb_stream_feed_dev/advance (host RNG in the reference's order "
                "on background threads, draws staged host->device on a side stream, per-chain L in "
-               "[5,20], chains restart inside the step they finish in; steady-state window of %d "
-               "batch steps%s)" % (window["steps"], "; row-sharded, draws shared through a /dev/shm "
-                                   "ring, NCCL all-reduce hooks" if world > 1 else ""))
-        torch.cuda.synchronize()
+               "[5,20], chains restart inside the step they finish in; %d proposals per chain; value = "
+               "steady-state window of %d batch steps, whole_run = fill + drain included%s)"
+               % (nprop, window["steps"], "; row-sharded, draws shared through a /dev/shm ring, %s exchange"
+                  % bt.exchange if world > 1 else ""))
         if os.environ.get("GI_STREAM_PROFILE") and rank == 0:
             print("stream profile (whole run, s):", bt.stream_profile, "steps", bt.stream_steps,
                   file=sys.stderr)
         # every chain takes one leapfrog step per batch step inside the window
-        steps_done, t_e2e, nprops_done = nch * window["steps"], window["t"], window["props"]
-        if world > 1:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-            t_e2e = float(t[0])
+        steps_done, t_e2e, nprops_done = nch * window["steps"], rmax(window["t"]), window["props"]
         e2e = {"value": steps_done / t_e2e, "unit": "leapfrog steps/s",
                "h2d_bytes_per_step": int(nprops_done * (8 * M + 12) / steps_done),
                "d2h_bytes_per_step": int(nprops_done * (8 * M + 80) / steps_done),
-               "proposals": nprops_done, "api": api}
-    elif world == 1:
-        np.random.seed(HMC["seed"])
-        x = x0
-        done, nprop = 0, 0
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        while done < args.steps:
-            L = min(np.random.randint(HMC["Lrange"][0], HMC["Lrange"][1] + 1), args.steps - done) or 1
-            x, U, dsyn, acc, Ud, Um = chain._leapfrog(x, dt, L, alpha)
-            done += L
-            nprop += 1
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        # per proposal: p0 (8M bytes) + u in; result struct + x (8M) + d (8N) out on accept
-        e2e = {"value": done / t_e2e, "unit": "leapfrog steps/s",
-               "h2d_bytes_per_step": int(nprop * (8 * M + 8) / done),
-               "d2h_bytes_per_step": int(nprop * (8 * M + 8 * N + 80) / done),
-               "proposals": nprop, "api": "HamitonianMC._leapfrog -> gi_hmc_propose"}
+               "proposals": nprops_done, "window_seconds": t_e2e,
+               "whole_run": {"value": chain_steps_whole / t_whole, "seconds": t_whole,
+                             "proposals": props_whole, "chain_steps": chain_steps_whole,
+                             "batch_steps": bt.stream_steps},
+               "api": api}
     else:
         np.random.seed(HMC["seed"])
         x = x0
         done, nprop = 0, 0
+        target = max(args.steps, 20 * 12)  # >= ~20 proposals
         torch.cuda.synchronize()
-        dist.barrier(group=group)
+        if world > 1:
+            dist.barrier(group=group)
         t0 = time.perf_counter()
-        while done < args.steps:
-            L = min(np.random.randint(HMC["Lrange"][0], HMC["Lrange"][1] + 1), args.steps - done) or 1
+        while done < target:
+            L = min(np.random.randint(HMC["Lrange"][0], HMC["Lrange"][1] + 1), target - done) or 1
             x, U, dsyn, acc, Ud, Um = chain._leapfrog(x, dt, L, alpha)
             done += L
             nprop += 1
         torch.cuda.synchronize()
-        dist.barrier(group=group)
-        t_e2e = time.perf_counter() - t0
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        e2e = {"value": done / float(t[0]), "unit": "leapfrog steps/s",
+        t_e2e = rmax(time.perf_counter() - t0)
+        # per proposal: p0 (8M bytes) + u in; result struct + x (8M) + d (8N) out on accept
+        e2e = {"value": done / t_e2e, "unit": "leapfrog steps/s",
                "h2d_bytes_per_step": int(nprop * (8 * M + 8) / done),
-               "d2h_bytes_per_step": int(nprop * (8 * M + 8 * n_local + 64) / done),
-               "proposals": nprop, "api": "HamitonianMC._leapfrog (row-sharded, NCCL all-reduce)"}
+               "d2h_bytes_per_step": int(nprop * (8 * M + 8 * n_local + 80) / done),
+               "proposals": nprop, "window_seconds": t_e2e,
+               "api": "HamitonianMC._leapfrog -> gi_hmc_propose" if world == 1 else
+                      "HamitonianMC._leapfrog (row-sharded, NCCL all-reduce)"}
 
-    asm_t = torch.tensor([t_asm, t_wgt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(asm_t, op=dist.ReduceOp.MAX, group=group)
-    t_asm, t_wgt = (float(v) for v in asm_t)
+    t_asm, t_wgt = rmax(t_asm), rmax(t_wgt)
+    ok = None
+    if selfcheck:
+        tol = {"aw_rows_vs_oracle": 1e-10, "aw_column_norms": 1e-12, "gemm_fwd_rows_vs_torch": 1e-12,
+               "gemm_adj_cols_vs_torch": 1e-12, "exchanged_gradient_vs_local_recompute": 1e-11}
+        for k in ("aw_rows_vs_oracle", "aw_column_norms"):
+            selfcheck[k] = rmax(selfcheck[k])
+        for k in ("gemm_fwd_rows_vs_torch", "gemm_adj_cols_vs_torch"):
+            if k in selfcheck:
+                selfcheck[k] = rmax(selfcheck[k])
+        vals = [selfcheck[k] / tol[k] for k in tol if k in selfcheck]
+        ok = bool(all(np.isfinite(v) and v < 1.0 for v in vals))
+        selfcheck.update(max_rel=max(selfcheck[k] for k in tol if k in selfcheck), ok=ok, tolerances=tol)
 
     out = None
     if rank == 0:
@@ -548,29 +676,45 @@ def gpu_arm(args):
         out = {
             "metric": "hmc_leapfrog_steps_per_s", "value": steps_per_s, "unit": "leapfrog steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": ms / timed_steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "timed_steps": timed_steps, "timed_seconds": ms * 1e-3,
             "config": {"workload": "%s%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, FP64 Aw "
                                    "%.1f GB row-sharded over %d GPU(s), Damping, %d chain(s) batched as columns; inputs "
-                                   "(%.1f GB per GPU per pass) exceed the 126 MB L2, no flush needed"
+                                   "(%.1f GB per GPU per pass) exceed the 126 MB L2, no flush needed; the "
+                                   "timed region repeats the %d steps %d time(s) to last >= %.0f s"
                                    % (args.workload, fallback_note, nz, ny, nx, M, N, 8e-9 * N * M, world, nch,
-                                      8e-9 * n_local * M),
+                                      8e-9 * n_local * M, args.steps, nrep, args.min_seconds),
                        "voxels": M, "observations": N, "chains": nch, "parallelism": "rows%d" % world},
             "batch_steps_per_s": steps_per_s / nch,
-            "gemv_hbm_GBps": (2 * bytes_pass * world) * steps_per_s / nch / 1e9,
+            # bytes of Aw streamed by the whole job per second (two passes per batch step, all GPUs);
+            # at C = 64 the passes are FP64-pipe bound, so this is NOT a GEMV bandwidth (see "c1")
+            "aw_streamed_GBps": (2 * bytes_pass * world) * steps_per_s / nch / 1e9,
             "assembly": {"mpairs_per_s": N * M / t_asm / 1e6, "seconds": t_asm,
                          "weighting_seconds": t_wgt},
             "roofline": {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": unit, "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get((args.workload, world, nch, dom)),
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "kernels": kern, "hbm_peak_GBps": hbm_peak},
             "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         }
+        if c1 is not None:
+            out["c1"] = c1
+        if exchange is not None:
+            out["exchange"] = exchange
+        if selfcheck:
+            out["selfcheck"] = selfcheck
         if cpu is not None:
             out["cpu_baseline"] = cpu
+    if bt is not None:
+        bt.close()
     if world > 1:
         dist.barrier(group=group)
         dist.destroy_process_group()
+    if ok is False:
+        if out is not None:
+            print(json.dumps(out))
+        raise SystemExit("bench.py: self-check FAILED: %s" % json.dumps(selfcheck))
     return out
 
 
@@ -586,9 +730,13 @@ def reference_arm(args):
     steps, warm = max(1, min(args.steps, 100)), max(0, min(args.warmup, 5))
     best = cpu_reference_arm(args.workload, args.cpu_rows, steps, warm=warm)
     v = best["value"]
+    # ms_per_step is what this run actually took per timed step (every chain advances one leapfrog
+    # step on the ROW SAMPLE); `value` is that rate scaled to the full observation count, whose
+    # per-chain-step time is reported beside it
     return {"impl": "reference", "metric": "hmc_leapfrog_steps_per_s", "value": v,
-            "unit": "leapfrog steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+            "unit": "leapfrog steps/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * best["chain_seconds"] / steps, "ms_per_chain_step_full_config": 1e3 / v,
+            "requested_steps": args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: Cartesian prisms %dx%dx%d (%d voxels) x %d obs, Damping; CPU "
                                    "reference path on a row sample" % (args.workload, nz, ny, nx, M, N),
@@ -613,6 +761,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",
                     help="profiling runs (ncu): skip the end-to-end arm, keep the device-timed region")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the bench-scale parity checks")
+    ap.add_argument("--no-c1", action="store_true", help="skip the single-chain (C = 1) block")
+    ap.add_argument("--min-seconds", type=float, default=2.0,
+                    help="the K timed steps are repeated until the timed region lasts this long")
+    ap.add_argument("--e2e-proposals", type=int, default=20, help="proposals per chain of the e2e run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = reference_arm(args) if args.impl == "reference" else gpu_arm(args)

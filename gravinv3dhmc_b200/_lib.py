@@ -30,7 +30,7 @@ class RegParams(C.Structure):
 
 class HmcConfig(C.Structure):
     _fields_ = [("N", C.c_int64), ("M", C.c_int64), ("ld", C.c_int64), ("fixed", C.c_int32),
-                ("reserved", C.c_int32), ("reg", RegParams)]
+                ("nocenter", C.c_int32), ("reg", RegParams)]
 
 
 class StreamRecord(C.Structure):
@@ -99,6 +99,7 @@ SIGNATURES = {
                                         C.POINTER(HmcResult)]),
     "gi_hmc_leapfrog_steps": (C.c_int, [_P, _P, C.c_int32, _D]),
     "gi_hmc_launch_count": (_I64, [_P]),
+    "gi_hmc_eval_path": (C.c_int32, [_P]),
     "gi_hmc_stream": (_P, [_P]),
     "gi_plan_batch_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(_I64)]),
     "gi_gemm_fwd": (C.c_int, [_P, _P, _P, _P, _P]),

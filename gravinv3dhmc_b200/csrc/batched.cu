@@ -465,7 +465,7 @@ misfit_batched_kernel(int mode, const double *__restrict__ part, int64_t nkc, in
     } else {
         s0 = sc[0];
     }
-    const double mean = s0 / (double)n_total;
+    const double mean = n_total > 0 ? s0 / (double)n_total : 0.0;  // n_total <= 0: no mean removal
     double s1 = 0.0;
     for (int64_t row = threadIdx.x; row < npad; row += 1024) {
         double rr = 0.0;
@@ -915,7 +915,7 @@ extern "C" int gi_data_sum_batched(gi_plan *p, const double *D, const double *fi
 extern "C" int gi_residual_batched(gi_plan *p, const double *D, const double *fix,
                                    const double *dobs_c, int64_t n_total, double *R, double *sums,
                                    void *stream) {
-    GI_REQUIRE(p && D && dobs_c && R && sums && n_total > 0 && p->nchains > 1,
+    GI_REQUIRE(p && D && dobs_c && R && sums && p->nchains > 1,
                "gi_residual_batched: bad argument");
     return launch_misfit_batched(p, 2, n_total, const_cast<double *>(D), fix, dobs_c, R, sums,
                                  (cudaStream_t)stream);
@@ -1061,7 +1061,7 @@ extern "C" int gi_hmcb_create(const gi_hmc_config *cfg, int32_t nchains, const d
     h->cfg = *cfg;
     h->G = G;
     h->nchains = nchains;
-    h->n_total = cfg->N;
+    h->n_total = cfg->nocenter ? 0 : cfg->N;
     h->npieces = 1;
     h->stream = (cudaStream_t)stream;
     rc = gi_plan_create(cfg->N, cfg->M, cfg->ld, nchains, &h->plan);
@@ -1115,7 +1115,7 @@ extern "C" int gi_hmcb_create(const gi_hmc_config *cfg, int32_t nchains, const d
         double *tmp = new double[N];
         long double acc = 0.0L;
         for (int64_t i = 0; i < N; ++i) acc += dobs_host[i];
-        const double mean = (double)(acc / (long double)N);
+        const double mean = cfg->nocenter ? 0.0 : (double)(acc / (long double)N);
         for (int64_t i = 0; i < N; ++i) tmp[i] = dobs_host[i] - mean;
         cudaError_t e = cudaMemcpyAsync(h->dobs_c, tmp, bn, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -1239,7 +1239,7 @@ static int hb_data_pass(gi_hmcb *h, const double *mw_in) {
         return rc;
     }
     if (!h->hook) {
-        rc = launch_misfit_batched(p, 0, p->nrows, h->d, fix, h->dobs_c, h->r, h->sums, s);
+        rc = launch_misfit_batched(p, 0, h->n_total, h->d, fix, h->dobs_c, h->r, h->sums, s);
         if (!rc) rc = launch_gemm_adj(p, h->G, h->r, h->gdata, s);
         h->launches += 3;
         return rc;
@@ -1274,6 +1274,7 @@ extern "C" int gi_hmcb_set_shard(gi_hmcb *h, int64_t n_total, const double *dobs
                                  gi_shard_hook hook, void *user) {
     GI_REQUIRE(h && hook && gdata_dev && red_dev && dobs_c_host, "gi_hmcb_set_shard: null pointer");
     GI_REQUIRE(n_total >= h->cfg.N, "gi_hmcb_set_shard: n_total is the GLOBAL observation count");
+    GI_REQUIRE(!h->cfg.nocenter, "gi_hmcb_set_shard: the joint data term is a single-GPU path");
     GI_REQUIRE(npieces >= 1 && h->cfg.ld % npieces == 0 && (npieces == 1 || (h->cfg.ld / npieces) % kAdjCols == 0),
                "gi_hmcb_set_shard: ld / npieces must be a multiple of 256");
     GI_CUDA(cudaMemcpyAsync(h->dobs_c, dobs_c_host, sizeof(double) * h->cfg.N, cudaMemcpyHostToDevice,
@@ -1324,6 +1325,7 @@ extern "C" int gi_hmcb_set_peer(gi_hmcb *h, gi_peer *peer, int64_t n_total, cons
     GI_REQUIRE(!h->hook && !h->peer, "gi_hmcb_set_peer: the handle already has an exchange path");
     GI_REQUIRE(peer->connected, "gi_hmcb_set_peer: call gi_peer_connect first");
     GI_REQUIRE(n_total >= h->cfg.N, "gi_hmcb_set_peer: n_total is the GLOBAL observation count");
+    if (h->cfg.nocenter) n_total = 0;  // no mean removal: nothing global about the residual
     GI_REQUIRE(peer->bytes >= gi_hmcb_peer_bytes(h, peer->world),
                "gi_hmcb_set_peer: the symmetric buffer is smaller than gi_hmcb_peer_bytes()");
     const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;

@@ -147,7 +147,7 @@ data_misfit_kernel(int mode, const double *__restrict__ part, int64_t nchunks, i
     } else {
         s0 = sums[0];
     }
-    const double mean = s0 / (double)n_total;
+    const double mean = n_total > 0 ? s0 / (double)n_total : 0.0;  // n_total <= 0: no mean removal
     double s1 = 0.0;
     for (int64_t row = threadIdx.x; row < nrows; row += kFinThreads) {
         const double t = d[row];
@@ -354,7 +354,7 @@ extern "C" int gi_data_sum(gi_plan *p, const double *d, const double *fix, doubl
 
 extern "C" int gi_residual(gi_plan *p, const double *d, const double *fix, const double *dobs_c,
                            int64_t n_total, double *r, double *sums, void *stream) {
-    GI_REQUIRE(p && d && dobs_c && r && sums && n_total > 0, "gi_residual: bad argument");
+    GI_REQUIRE(p && d && dobs_c && r && sums, "gi_residual: bad argument");
     data_misfit_kernel<<<1, kFinThreads, 0, (cudaStream_t)stream>>>(
         2, nullptr, 0, p->nrows, n_total, const_cast<double *>(d), fix, dobs_c, r, sums);
     GI_LAUNCH_CHECK();
@@ -474,16 +474,20 @@ static void hmc_free(gi_hmc *h) {
     delete h;
 }
 
-// The fused single-pass evaluation pays one cross-SM hand-off per observation row, so it only wins
-// when a row strip is worth streaming: kernels of >= 1 GB by default (GI_FUSED_GEMV=1 forces it on
-// for any shape that fits, =0 switches it off).  Falls back silently to the two-pass kernels.
+// The fused single-pass evaluation pays one cross-SM hand-off per observation row (~1 us), so it only
+// wins when a row is worth that: the two GEMV passes stream a row in 16 M bytes / 7.3 TB/s, which
+// exceeds the hand-off above M ~ 460 000 voxels (measured: c5, M = 2^20: 27.0 vs 37.4 ms per
+// evaluation; mid, M = 2^17: 4.1 vs 1.2 ms).  Default: rows of >= 4 MB (M >= 524 288) and kernels of
+// >= 1 GB (GI_FUSED_GEMV=1 forces it on for any shape that fits, =0 switches it off).  The two-pass
+// kernels (1.12 x the measured copy bandwidth) serve every other shape, including strips that do not
+// fit one SM's shared memory (M > 148 x 7168); gi_hmc_eval_path reports which one is in use.
 static bool fused_ready(gi_hmc *h) {
     if (h->fused_state >= 0) return h->fused_state == 1;
     h->fused_state = 0;
     const char *env = getenv("GI_FUSED_GEMV");
     if (env && env[0] == '0') return false;
     const bool force = env && env[0] == '1';
-    if (!force && (double)h->cfg.N * (double)h->cfg.ld * 8.0 < 1e9) return false;
+    if (!force && ((double)h->cfg.N * (double)h->cfg.ld * 8.0 < 1e9 || h->cfg.M < (1 << 19))) return false;
     if (gi_fused_create(h->cfg.N, h->cfg.M, h->cfg.ld, h->G, h->stream, &h->fused) != GI_OK) {
         h->fused = nullptr;
         return false;
@@ -562,7 +566,7 @@ extern "C" int gi_hmc_create(const gi_hmc_config *cfg, const double *G, const do
         double *tmp = new double[cfg->N];
         long double acc = 0.0L;
         for (int64_t i = 0; i < cfg->N; ++i) acc += dobs_host[i];
-        const double mean = (double)(acc / (long double)cfg->N);
+        const double mean = cfg->nocenter ? 0.0 : (double)(acc / (long double)cfg->N);
         for (int64_t i = 0; i < cfg->N; ++i) tmp[i] = dobs_host[i] - mean;
         cudaError_t e = cudaMemcpyAsync(h->dobs_c, tmp, bn, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -599,6 +603,7 @@ static int grad_eval_and_update(gi_hmc *h, const double *x_in, const double *mw_
                                 int advance) {
     gi_plan *p = h->plan;
     cudaStream_t s = h->stream;
+    const int64_t ncen = h->cfg.nocenter ? 0 : p->nrows;  // rows the mean is taken over (0: no mean removal)
     int rc;
     if (h->wv_kind) {
         // d = Awcp @ DWT(mw)  (compressor1D.py:45-60 / compressor3D.py:47-68)
@@ -609,15 +614,16 @@ static int grad_eval_and_update(gi_hmc *h, const double *x_in, const double *mw_
         if (rc) return rc;
         rc = gi_csr_spmv(h->wv_indptr, h->wv_indices, h->wv_data, p->nrows, h->wv_coef, h->d, s);
         if (rc) return rc;
-        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, p->nrows, h->d,
+        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, ncen, h->d,
                                                      h->cfg.fixed ? h->fix : nullptr, h->dobs_c,
                                                      h->r, h->sums);
         h->launches += (h->wv_kind == 1 ? 2 : 7);
     } else if (fused_ready(h)) {
         // d, Aw^T r in ONE pass over Aw (fused.cu); then U_data from d, and the usual fused update
-        rc = gi_fused_pass(h->fused, mw_in, h->dobs_c, h->cfg.fixed ? h->fix : nullptr, 1, h->d, h->gfused, s);
+        rc = gi_fused_pass(h->fused, mw_in, h->dobs_c, h->cfg.fixed ? h->fix : nullptr, h->cfg.nocenter ? 0 : 1,
+                           h->d, h->gfused, s);
         if (rc) return rc;
-        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, p->nrows, h->d,
+        data_misfit_kernel<<<1, kFinThreads, 0, s>>>(3, nullptr, 0, p->nrows, ncen, h->d,
                                                      h->cfg.fixed ? h->fix : nullptr, h->dobs_c,
                                                      h->r, h->sums);
         GI_LAUNCH_CHECK();
@@ -629,7 +635,7 @@ static int grad_eval_and_update(gi_hmc *h, const double *x_in, const double *mw_
         rc = launch_fwd_partial(p, h->G, mw_in, s);
         if (rc) return rc;
         data_misfit_kernel<<<1, kFinThreads, 0, s>>>(0, p->fwd_part, p->fwd_nchunks, p->nrows,
-                                                     p->nrows, h->d, h->cfg.fixed ? h->fix : nullptr,
+                                                     ncen, h->d, h->cfg.fixed ? h->fix : nullptr,
                                                      h->dobs_c, h->r, h->sums);
     }
     GI_LAUNCH_CHECK();
@@ -836,6 +842,12 @@ extern "C" int gi_hmc_set_wavelet(gi_hmc *h, int32_t kind, int32_t nz, int32_t n
 }
 
 extern "C" int64_t gi_hmc_launch_count(const gi_hmc *h) { return h ? h->launches : 0; }
+// 0: the two GEMV passes, 1: the single-pass evaluation (fused.cu), 2: wavelet-compressed forward
+extern "C" int32_t gi_hmc_eval_path(gi_hmc *h) {
+    if (!h) return -1;
+    if (h->wv_kind) return 2;
+    return fused_ready(h) ? 1 : 0;
+}
 extern "C" void *gi_hmc_stream(const gi_hmc *h) { return h ? (void *)h->stream : nullptr; }
 
 // =============================================================================================

@@ -83,7 +83,9 @@ class BlockEngine:
 
             self._fused = False
             env = os.environ.get("GI_FUSED_GEMV", "")
-            big = self.n_local * self.ld * 8.0 >= 1e9
+            # rows of >= 4 MB in kernels of >= 1 GB: below that the per-row hand-off of the single-pass
+            # kernel costs more than the second pass it saves (csrc/leapfrog.cu: fused_ready)
+            big = self.n_local * self.ld * 8.0 >= 1e9 and self.M >= (1 << 19)
             if env != "0" and (big or env == "1"):
                 h = C.c_void_p()
                 if self.L.gi_fused_create(self.n_local, self.M, self.ld, _lib.ptr(self.Aw),
@@ -117,7 +119,8 @@ class BlockEngine:
         fused = self._fused_handle() if dpre is None else False
         if fused:
             # d and Aw_local^T (e - mean_local) in ONE pass over this rank's rows
-            _lib.check(L.gi_fused_pass(fused, p(mw), p(self.dobs_c), p(self.fix), 1, p(self.d), p(self.g), s),
+            _lib.check(L.gi_fused_pass(fused, p(mw), p(self.dobs_c), p(self.fix), 1 if self.n_total > 0 else 0,
+                                       p(self.d), p(self.g), s),
                        "gi_fused_pass")
         elif dpre is not None:
             self.d.copy_(dpre)

@@ -367,8 +367,11 @@ class HMCBatch:
                  save_folder="mychain", rng="numpy", quiet=False, driver="auto"):
         if constraint not in _lib.CONSTRAINTS:
             raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
-        if regularization not in _lib.REG_KINDS:
+        extra = getattr(model, "extra_regs", {})   # JointModule: "MS1" / "MStry" (potential.py:1701-1736)
+        if regularization not in _lib.REG_KINDS and regularization not in extra:
             raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
+        if regularization in ("Smoothness", "TV") and getattr(model, "nocenter", False):
+            raise AttributeError("'JointModule' object has no attribute 'fd3d'")  # potential.py:1753,1765
         if not 2 <= int(nchains) <= 64:
             raise ValueError("HMCBatch: 2..64 chains per batch (use hmc.HMCSample for one chain)")
         if model.wavelet:
@@ -406,7 +409,8 @@ class HMCBatch:
         else:
             x0 = mw
         self.x = np.ascontiguousarray(np.tile(x0, (self.nchains, 1)))
-        self.reg = reg_params(regularization, constraint, model.mshape, RegulFactor, beta, log_factor)
+        self.reg = reg_params(extra.get(regularization, regularization), constraint, model.mshape, RegulFactor,
+                              beta, log_factor)
         sharded = getattr(model, "world", 1) > 1
         # row-sharded batches: "device" = the C loop, exchanging through peer memory over NVLink
         # (csrc/peer.cu; GI_SHARD_EXCHANGE=nccl or driver="device-nccl": NCCL all-reduce hooks instead);
@@ -426,10 +430,12 @@ class HMCBatch:
         L = _lib.lib()
         m = model
         lo, hi = m.rows if sharded else (0, m.n_total)
-        cfg = _lib.HmcConfig(hi - lo, m.M, m.ld, 1 if m.fixed else 0, 0, self.reg)
+        cfg = _lib.HmcConfig(hi - lo, m.M, m.ld, 1 if m.fixed else 0,
+                             1 if getattr(m, "nocenter", False) else 0, self.reg)
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        self._host = dict(dobs=f(m.dobs[lo:hi]), low=f(self.low), high=f(self.high),
-                          apr=f(self.aprior_model), wmsq=f(m.WmSquare.diagonal()))
+        self._host = dict(dobs=f(getattr(m, "dobs_sampler", m.dobs)[lo:hi]), low=f(self.low), high=f(self.high),
+                          apr=f(self.aprior_model),
+                          wmsq=f(np.ones(m.M) if regularization == "MStry" else m.WmSquare.diagonal()))
         fix = f(np.asarray(m.grav_fix, dtype=np.float64)[lo:hi]) if m.fixed else None
         h = C.c_void_p()
         _lib.check(L.gi_hmcb_create(C.byref(cfg), self.nchains, _lib.ptr(m.Aw_pad),

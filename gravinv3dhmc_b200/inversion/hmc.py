@@ -66,14 +66,17 @@ class HamitonianMC:
 
     # ---- device handle ----------------------------------------------------------------------
     def _reg(self, alpha):
-        return reg_params(self.regularization, self.constraint, self.model.mshape, alpha, self.beta,
-                          self.log_factor)
+        # JointModule also knows "MS1" / "MStry" (potential.py:1701-1736): MS kernels, see _ensure_handle
+        name = getattr(self.model, "extra_regs", {}).get(self.regularization, self.regularization)
+        return reg_params(name, self.constraint, self.model.mshape, alpha, self.beta, self.log_factor)
 
     def _sharded(self):
         return getattr(self.model, "world", 1) > 1
 
     def _ensure_handle(self, alpha):
         m = self.model
+        if self.regularization in ("Smoothness", "TV") and getattr(m, "nocenter", False):
+            raise AttributeError("'JointModule' object has no attribute 'fd3d'")  # potential.py:1753,1765
         if self.regularization in ("Smoothness", "TV") and int(np.prod(m.mshape)) != m.M:
             raise ValueError("Smoothness/TV are defined on the full (nz, ny, nx) grid and cannot "
                              "be used with a topography-carved model")
@@ -86,10 +89,12 @@ class HamitonianMC:
             return
         _lib.require_cuda()
         L = _lib.lib()
-        cfg = _lib.HmcConfig(m.n_total, m.M, m.ld, 1 if m.fixed else 0, 0, self._reg(alpha))
+        cfg = _lib.HmcConfig(m.n_total, m.M, m.ld, 1 if m.fixed else 0,
+                             1 if getattr(m, "nocenter", False) else 0, self._reg(alpha))
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        self._host = dict(dobs=f(m.dobs), low=f(self.low), high=f(self.high),
-                          apr=f(self.aprior_model), wmsq=f(m.WmSquare.diagonal()))
+        wmsq = np.ones(m.M) if self.regularization == "MStry" else m.WmSquare.diagonal()
+        self._host = dict(dobs=f(getattr(m, "dobs_sampler", m.dobs)), low=f(self.low), high=f(self.high),
+                          apr=f(self.aprior_model), wmsq=f(wmsq))
         fix = f(m.grav_fix) if m.fixed else None
         if fix is not None:
             self._host["fix"] = fix
@@ -267,7 +272,7 @@ def setup_chain(model, delta, Lrange, initial_model, aprior_model, boundaries, c
     """The chain object of hmc.py:358-401 (everything HMCSample does before `chain.sample`)."""
     if constraint not in _lib.CONSTRAINTS:
         raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
-    if regularization not in _lib.REG_KINDS:
+    if regularization not in _lib.REG_KINDS and regularization not in getattr(model, "extra_regs", {}):
         raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
     chain = HamitonianMC(model)
     chain.myrank = myrank

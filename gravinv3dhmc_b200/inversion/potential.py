@@ -252,7 +252,7 @@ class GravMagModule:
         return None
 
     def _evaluate(self, mw, mwapr, alpha, regularization, beta, constraint="mandatory",
-                  log_factor=0.0):
+                  log_factor=0.0, wmsq=None):
         """(U, grad, dpre, Ud, Um) at the weighted model `mw` (numpy)."""
         eng = self.engine()
         reg = reg_params(regularization, "mandatory", self.mshape, alpha, beta, log_factor)
@@ -262,8 +262,8 @@ class GravMagModule:
         mw_d, apr_d = eng.vec(mw), eng.vec(mwapr)
         eng.data_pass(mw_d, self._forward(mw_d))
         pm, grad = eng.vec(), eng.vec()
-        eng.update(reg, mw_d, mw_d, apr_d, self.wmsq_dev, None, None, pm, None, None, grad, 0.0,
-                   0.0, 0)
+        eng.update(reg, mw_d, mw_d, apr_d, self.wmsq_dev if wmsq is None else wmsq, None, None, pm, None,
+                   None, grad, 0.0, 0.0, 0)
         sums = eng.sums.cpu().numpy()
         Ud, Um = float(sums[1]), float(sums[2])
         return (Ud + alpha * Um, grad[: self.M].cpu().numpy(), eng.d.cpu().numpy(), Ud, Um)
@@ -325,3 +325,165 @@ class GravMagModule:
         elif constraint != "mandatory":
             raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
         return self.data_all(x)[1]
+
+
+class JointModule(GravMagModule):
+    """Joint gravity (gz) + magnetic (total-field anomaly) model on ONE prism mesh: mirror of the
+    reference's `JointModule` (inversion/potential.py:847-1812) -- same constructor arguments
+    (`dobs_gz, dobs_tf, mrange, mspacing, obsurface, mratio, coordinate, njobs, mangle, wavelet,
+    mtopo=`), same attributes (`kernel_gz, kernel_tf, A, Aw, dobs, dobsw, Wm, WmInv, WmSquare, Wb,
+    meshrho, meshmag, mshape, mxs, mys, mzs`), same sampler duck type (`kernelw`, `misfit_and_grad`).
+
+    The kernel is the block matrix [[K_gz, 0], [0, K_tf]] of (2N x 2M) (potential.py:938-941; the
+    reference holds it dense, so does this class -- on the device); the model vector is
+    [density (M) | magnetisation intensity (M)].  `weightKDM` (potential.py:1003-1067): Wm = column
+    norms of A, Wb = 1 on the gz rows and std(K_gz) / std(K_tf) on the tf rows, Aw = Wb A Wm^-1,
+    dobsw = Wb [dobs_gz | dobs_tf].  The data term has NO mean removal (`data_all`,
+    potential.py:1665-1680: |Aw mw - dobsw|^2), unlike `GravMagModule`.
+
+    Reference behaviour kept: `coordinate="spherical"` fails with UnboundLocalError (`kernel_tf` is never
+    assigned there, potential.py:885-899); Smoothness / TV fail with AttributeError (`self.fd3d`
+    does not exist on JointModule, potential.py:1753,1765); `regulization` also accepts "MS1" (the
+    matrix form of MS: same value and gradient) and "MStry" (MS without the Wm weighting,
+    potential.py:1701-1736)."""
+
+    nocenter = True   # sampler handles: r = d - dobs (gi_hmc_config.nocenter)
+    extra_regs = {"MS1": "MS", "MStry": "MS"}
+
+    def __init__(self, dobs_gz, dobs_tf, mrange, mspacing, obsurface, mratio=1, coordinate="cartesian",
+                 njobs=1, mangle=(90, 0), wavelet=False, **kwargs):
+        from ..utils import ang2vec, dircos
+
+        self.group = kwargs.pop("group", None)
+        self.verbose = kwargs.pop("verbose", True)
+        self.timing = {}
+        self.dobs_gz = np.asarray(dobs_gz, dtype=np.float64)
+        self.dobs_tf = np.asarray(dobs_tf, dtype=np.float64)
+        self.mrange, self.mspacing, self.mratio = mrange, mspacing, mratio
+        self.lonobs, self.latobs, self.heightobs = obsurface[0], obsurface[1], obsurface[2]
+        self.inc, self.dec = mangle[0], mangle[1]
+        self.njobs = njobs
+        self.topocarve = False
+        self.wavelet = wavelet
+        self.fixed, self.grav_fix = False, []
+        self.coordinate = coordinate
+        self.weightfactor = 0.5
+        if coordinate == "spherical":
+            self._say("Joint inversion in {} coordinate.".format(coordinate))
+            # potential.py:885-899 assembles kernel_gz only; `self.kernel_tf = kernel_tf` then fails
+            raise UnboundLocalError("cannot access local variable 'kernel_tf' where it is not associated "
+                                    "with a value")
+        if coordinate != "cartesian":
+            raise ValueError("Please choose coordinate from(cartesian, spherical)!")  # potential.py:923
+        self._say("Joint inversion in {} coordinate.".format(coordinate))
+        mesh = mesher.PrismMesh(mrange, mspacing, mratio)
+        for key, value in kwargs.items():  # potential.py:902-906: any extra kwarg = topography
+            self.topocarve = True
+            self.mask = mesh.carvetopo(value[0], value[1], value[2])
+        self.mesh = mesh
+        self.meshrho, self.meshmag = mesh.copy(), mesh.copy()
+        self.meshrho.addprop("density", np.zeros(mesh.size))
+        self.meshmag.addprop("magnetization", ang2vec(np.zeros(mesh.size), self.inc, self.dec))
+        table = mesh.bounds_table()
+        n = len(self.lonobs)
+        out = prism.assemble_grid(self.lonobs, self.latobs, self.heightobs, mesh)
+        Kgz, Mc = out if out is not None else prism.assemble(self.lonobs, self.latobs, self.heightobs, table)
+        Ktf, _ = prism.assemble_field("tf", self.lonobs, self.latobs, self.heightobs, table,
+                                      vec=dircos(self.inc, self.dec))
+        torch = _lib.require_cuda()
+        self.Mcells = Mc
+        self.M, self.n_total = 2 * Mc, 2 * n
+        self.ld = _lib.padded_ld(self.M)
+        self.rank, self.world, self.rows = 0, 1, (0, self.n_total)
+        A = torch.zeros((self.n_total, self.ld), dtype=torch.float64, device=Kgz.device)
+        A[:n, :Mc] = Kgz[:, :Mc]            # potential.py:938-941 np.block
+        A[n:, Mc:2 * Mc] = Ktf[:, :Mc]
+        self.kernel_gz, self.kernel_tf = Kgz[:, :Mc], Ktf[:, :Mc]
+        self.mshape = mesh.shape
+        self.mxs, self.mys, self.mzs = mesh.get_xs(), mesh.get_ys(), mesh.get_zs()
+        self.Aw_pad = A
+        self.weightKDM()
+        self._engine = None
+        self._mg_cache = {}
+        if wavelet == "1D":
+            from ..gravmag import compressor1D as cp1D
+
+            self._say("Using {} wavelet to compress kernel.".format(wavelet))
+            self.Awcp = cp1D.kernelcompressor(self.Aw)
+        elif wavelet == "3D":
+            # potential.py:951: cp3D reshapes every 2M-long row to (nz, ny, nx)
+            raise ValueError("cannot reshape array of size {} into shape {}".format(self.M, tuple(self.mshape)))
+
+    @property
+    def A(self):
+        """the un-weighted block kernel (potential.py:942), rebuilt on demand: A = Wb^-1 Aw Wm"""
+        n, Mc = self.n_total // 2, self.Mcells
+        A = self.Aw_pad[:, : self.M] * self.wm_dev[: self.M]
+        A[n:] /= self._wb_ratio
+        return A
+
+    def weightKDM(self):
+        """potential.py:1003-1067, in place on the device"""
+        torch = _lib.require_cuda()
+        L, s = _lib.lib(), _lib.stream_ptr()
+        A = self.Aw_pad
+        n2, ld = (int(v) for v in A.shape)
+        n = n2 // 2
+        f64 = dict(dtype=torch.float64, device=A.device)
+        sumsq = torch.zeros(ld, **f64)
+        _lib.check(L.gi_colsumsq(_lib.ptr(A), n2, self.M, ld, _lib.ptr(sumsq), 0, s), "gi_colsumsq")
+        wm, wminv, wmsq = (torch.zeros(ld, **f64) for _ in range(3))
+        _lib.check(L.gi_weights_from_sumsq(_lib.ptr(sumsq), self.M, 0.5, _lib.ptr(wm), _lib.ptr(wminv),
+                                           _lib.ptr(wmsq), s), "gi_weights_from_sumsq")
+        # Wb (potential.py:1041-1052, "method3"): the population standard deviations of the two kernels
+        std_gz = float(self.kernel_gz.std(unbiased=False))
+        std_tf = float(self.kernel_tf.std(unbiased=False))
+        self._wb_ratio = std_gz / std_tf
+        wb = np.append(np.ones_like(self.dobs_gz), np.ones_like(self.dobs_tf) * (std_gz / std_tf))
+        A[n:] *= self._wb_ratio            # Aw = (Wb A) WmInv: rows first, then columns
+        _lib.check(L.gi_scale_columns(_lib.ptr(A), n2, self.M, ld, _lib.ptr(wminv), s), "gi_scale_columns")
+        _lib.sync()
+        self.wm_dev, self.wminv_dev, self.wmsq_dev = wm, wminv, wmsq
+        self.Aw = A[:, : self.M]
+        row = np.arange(0, self.M)
+        diag = lambda v, m: coo_matrix((v, (np.arange(m), np.arange(m))), shape=(m, m)).tocsr()
+        self.Wm = diag(wm[: self.M].cpu().numpy(), self.M)
+        self.WmInv = diag(wminv[: self.M].cpu().numpy(), self.M)
+        self.WmSquare = diag(wmsq[: self.M].cpu().numpy(), self.M)
+        self.Wb = diag(wb, n2)
+        self.dobs = np.append(self.dobs_gz, self.dobs_tf)
+        self.dobsw = self.Wb @ self.dobs
+        self.dobs_sampler = self.dobsw     # what the data term compares with (potential.py:1677)
+
+    def forward(self, model):
+        """potential.py:1069-1074: un-weighted kernel times un-weighted model"""
+        torch = _lib.require_cuda()
+        m = torch.as_tensor(np.asarray(model, dtype=np.float64), device=self.Aw_pad.device)
+        return (self.A @ m).cpu().numpy()
+
+    def engine(self):
+        if self._engine is None:
+            # no mean removal: dobs_mean = 0 and n_total = 0 switch the centring off (gi_residual)
+            self._engine = BlockEngine(self.Aw_pad, self.M, self.dobsw, 0.0, 0, None, None)
+        return self._engine
+
+    def misfit_and_grad(self, x, mwapr, low, high, constraint, log_fator, alpha, regulization="Damping",
+                        beta=0.01):
+        """potential.py:1775-1812"""
+        x = np.asarray(x, dtype=np.float64)
+        if constraint == "logarithmic":
+            mw = (low + high * np.e ** (log_fator * x)) / (1 + np.e ** (log_fator * x))
+        elif constraint == "mandatory":
+            mw = x
+        else:
+            raise ValueError("Please choose right boundary constraint(mandatory, logarithmic)!")
+        if regulization in ("Smoothness", "TV"):
+            raise AttributeError("'JointModule' object has no attribute 'fd3d'")  # potential.py:1753,1765
+        if regulization not in ("MS", "MS1", "MStry", "Damping"):
+            raise ValueError("Please choose regularization from 'MS','Damping', 'Smoothness', 'TV'.")
+        wmsq = self.wmsq_dev
+        if regulization == "MStry":
+            wmsq = self.wmsq_dev.clone()
+            wmsq[: self.M] = 1.0
+        return self._evaluate(mw, mwapr, alpha, self.extra_regs.get(regulization, regulization), beta,
+                              wmsq=wmsq)

@@ -175,6 +175,7 @@ int gi_data_sum(gi_plan *plan, const double *d_dev, const double *fix_dev, doubl
                 void *stream);
 /* r[l] = (d[l] + fix[l] - mean) - dobs_c[l] with mean = sums_dev[0] / n_total (sums_dev[0] is
  * the sum over ALL ranks' rows, n_total the global observation count);  sums_dev[1] = sum r^2. */
+/* n_total <= 0: no mean removal (r = d + fix - dobs_c with dobs_c = dobs) */
 int gi_residual(gi_plan *plan, const double *d_dev, const double *fix_dev,
                 const double *dobs_c_dev, int64_t n_total, double *r_dev, double *sums_dev,
                 void *stream);
@@ -228,7 +229,8 @@ typedef struct gi_hmc gi_hmc;
 typedef struct {
     int64_t N, M, ld;
     int32_t fixed; /* potential.py:699-703: add grav_fix to the forward data */
-    int32_t reserved;
+    int32_t nocenter; /* 0: r = (d - mean d) - (dobs - mean dobs) (GravMagModule, potential.py:706);
+                         1: r = d - dobs (JointModule.data_all, potential.py:1665-1680) */
     gi_reg_params reg;
 } gi_hmc_config;
 
@@ -276,6 +278,9 @@ int gi_hmc_set_wavelet(gi_hmc *h, int32_t kind, int32_t nz, int32_t ny, int32_t 
                        int64_t ncoef);
 /* kernels launched by this handle since creation */
 int64_t gi_hmc_launch_count(const gi_hmc *h);
+/* which gradient evaluation the handle uses: 0 = the two GEMV passes, 1 = the single-pass evaluation
+ * (rows of >= 4 MB in kernels of >= 1 GB whose column strip fits one SM), 2 = wavelet-compressed forward */
+int32_t gi_hmc_eval_path(gi_hmc *h);
 void *gi_hmc_stream(const gi_hmc *h);
 
 /* ---- C independent chains batched as columns (FP64 tensor-core contractions) ----------------- */

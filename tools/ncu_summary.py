@@ -58,5 +58,43 @@ def rep(path):
         print()
 
 
+def traffic(path, workload, n_gpus, chains, out="profiles/r02_traffic.json"):
+    """add / replace the entries of profiles/r02_traffic.json for the kernels of one --set full report:
+    python tools/ncu_summary.py traffic <file.ncu-rep> <workload> <n_gpus> <chains>"""
+    import json
+    import os
+    import re
+
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True,
+                         check=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    H, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    doc = json.load(open(out)) if os.path.exists(out) else {"entries": []}
+    seen = {}
+    for r in rows[2:]:
+        name = re.sub(r"<.*", "", r[H.index("Kernel Name")].split("(")[0]).split("::")[-1].replace("_kernel", "")
+        vals = []
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = H.index(k)
+            vals.append(float(r[i].replace(",", "")) * scale[units[i]])
+        if any(v != v for v in vals):
+            continue  # counters overflowed (nan)
+        seen.setdefault(name, []).append((vals, r[H.index("gpu__time_duration.sum")]))
+    for name, caps in seen.items():
+        rd = sum(v[0][0] for v in caps) / len(caps)
+        wr = sum(v[0][1] for v in caps) / len(caps)
+        e = {"workload": workload, "n_gpus": int(n_gpus), "chains": int(chains), "kernel": name,
+             "dram_bytes": rd + wr,
+             "metric": "dram__bytes_read.sum %.6f GB + dram__bytes_write.sum %.6f MB (mean of %d launches)"
+                       % (rd / 1e9, wr / 1e6, len(caps)),
+             "source": "%s (ncu --set full --clock-control none)" % path}
+        doc["entries"] = [x for x in doc["entries"]
+                          if (x["workload"], x["n_gpus"], x["chains"], x["kernel"]) !=
+                          (workload, int(n_gpus), int(chains), name)] + [e]
+        print(e)
+    json.dump(doc, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "rep": rep, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
