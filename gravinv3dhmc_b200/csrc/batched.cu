@@ -24,6 +24,7 @@
 // The MMA k-slot <-> memory index assignment is permuted (a sum is order-free as long as A and B
 // agree) so that each thread's fragment elements are adjacent in shared memory.
 // Deterministic: fixed tile -> slot mapping, no floating-point atomics.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1611,6 +1612,20 @@ extern "C" int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t 
 // =============================================================================================
 // streaming sampler (see include/gravinv_b200.h)
 // =============================================================================================
+// Wait for a stream WITHOUT spinning: cudaStreamSynchronize busy-polls by default, which takes a whole
+// host core for the ~65 ms a streaming call lasts -- cores the draw workers need (every proposal's
+// momentum is 2^20 MT19937 normals generated on the host in the reference's RNG order).
+static cudaError_t sync_sleeping(cudaStream_t s) {
+    static thread_local cudaEvent_t ev = nullptr;
+    static const bool spin = getenv("GI_SLEEPING_SYNC") && getenv("GI_SLEEPING_SYNC")[0] == '0';
+    if (spin) return cudaStreamSynchronize(s);
+    cudaError_t e = cudaSuccess;
+    if (!ev) e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, s);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+    return e;
+}
+
 extern "C" int gi_hmcb_stream_begin(gi_hmcb *h, double dt) {
     GI_REQUIRE(h, "gi_hmcb_stream_begin: null handle");
     GI_REQUIRE(h->has_state, "gi_hmcb_stream_begin: call gi_hmcb_set_state first");
@@ -1843,7 +1858,7 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         gi_stream_record *tmp = new gi_stream_record[nrec];
         cudaError_t e = cudaMemcpyAsync(tmp, h->rec_dev, sizeof(gi_stream_record) * nrec,
                                         cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = sync_sleeping(s);
         if (e != cudaSuccess) { delete[] tmp; return cuda_fail(e, "records", __FILE__, __LINE__); }
         for (int i = 0; i < nrec; ++i) {
             records[i] = tmp[i];
@@ -1852,10 +1867,10 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         }
         delete[] tmp;
     } else {
-        GI_CUDA(cudaStreamSynchronize(s));
+        GI_CUDA(sync_sleeping(s));
     }
     if (h->copies_pending) {
-        GI_CUDA(cudaStreamSynchronize(h->copy_stream));
+        GI_CUDA(sync_sleeping(h->copy_stream));
         h->copies_pending = false;
     }
     *nrecords = nrec;

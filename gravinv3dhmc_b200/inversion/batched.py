@@ -325,6 +325,8 @@ class _Stager(threading.Thread):
         try:
             torch.cuda.set_device(self.dev)
             side = torch.cuda.Stream(self.dev)
+            # a sleeping wait: the cores belong to the draw workers (GI_SLEEPING_SYNC=0: spin)
+            landed = torch.cuda.Event(blocking=os.environ.get("GI_SLEEPING_SYNC", "1") != "0")
             count = [0] * self.nc
             with torch.cuda.stream(side):
                 while True:
@@ -338,7 +340,8 @@ class _Stager(threading.Thread):
                     row = ring.data[c, k % ring.depth]
                     L, u = int(row[M]), float(row[M + 1])
                     buf.copy_(ring.tdata[c, k % ring.depth], non_blocking=True)
-                    side.synchronize()  # the side stream only
+                    landed.record(side)
+                    landed.synchronize()  # the side stream only, without spinning
                     ring.release(c, k)
                     self.bytes_h2d += 8 * (M + 2)
                     with self.cv:
@@ -644,8 +647,11 @@ class HMCBatch:
                 os.unlink(name[0])  # every rank has it mapped; the memory lives until they unmap
         else:
             ring = _DrawRing(nc, M)
-        # host threads for the draws: this rank's share of the cores, minus the sampler and stager threads
-        nw = max(1, min(8, (os.cpu_count() or 2) // max(world, 1) - 2))
+        # host threads for the draws: this rank's share of the cores minus one (the sampler and the stager
+        # threads sleep in their waits, see sync_sleeping in csrc/batched.cu)
+        nw = max(1, min(8, (os.cpu_count() or 2) // max(world, 1) - 1))
+        if os.environ.get("GI_DRAW_WORKERS"):
+            nw = max(1, int(os.environ["GI_DRAW_WORKERS"]))
         self._ahead = _DrawAhead(self.streams, self.Lrange, M, self.Sigma, ring, nworkers=nw, owned=owned)
         self._ahead.limit = limit
         self._ahead.start()

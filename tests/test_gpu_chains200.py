@@ -109,7 +109,10 @@ def run_stream(model, g, p, reg, init, apr, b, tmp_path, tag):
                           p["alpha"], reg, p["beta"], p["seed"], p["Sigma"],
                           save_folder=str(tmp_path / ("t" + tag)), quiet=True)
     bt.output = "binary"
-    bt.stream(200, 0)
+    # the sibling chain of the batch is not part of the golden: cap it at the golden chain's proposal
+    # count (the reference's rank-0 MS chain on c3, e.g., stops accepting after 11 samples and would
+    # -- faithfully -- never reach 200)
+    bt.stream(200, 0, max_proposals=int(g["log"].shape[0]))
     folder = tmp_path / ("t%s%d" % (tag, c))
     mis = np.fromfile(folder / "misfit.f64").reshape(-1, 7)
     mod = np.fromfile(folder / "model.f64").reshape(200, -1)

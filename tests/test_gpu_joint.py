@@ -109,7 +109,7 @@ def test_chain_matches_reference(joint, reg, alpha, tmp_path):
     # the same chain as rank 0 of a batch (DMMA contractions, no mean removal in the batched misfit)
     bt = batched.HMCSampleBatch(model, 2, 8, 0, 0.02, [3, 8], np.ones(M) * 0.001, np.ones(M) * 0.001, b,
                                 "mandatory", 1000, dobs, "Fixed", 0.8, alpha, reg, 0.001, 21, 0.05,
-                                save_folder=str(tmp_path / "jb"), quiet=True)
+                                save_folder=str(tmp_path / "jb"), quiet=True, max_proposals=len(log))
     assert [(L, int(a)) for L, a in bt.proposals[0]][: len(log)] == [(int(L), int(a)) for L, a in log[:, :2]]
     mis = np.loadtxt(tmp_path / "jb0" / "misfit.dat", ndmin=2)
     assert np.allclose(mis, g["chain_%s_misfit" % reg], rtol=0, atol=2e-8)

@@ -73,7 +73,8 @@ def traffic(path, workload, n_gpus, chains, out="profiles/r02_traffic.json"):
     doc = json.load(open(out)) if os.path.exists(out) else {"entries": []}
     seen = {}
     for r in rows[2:]:
-        name = re.sub(r"<.*", "", r[H.index("Kernel Name")].split("(")[0]).split("::")[-1].replace("_kernel", "")
+        name = re.sub(r"<.*", "", r[H.index("Kernel Name")].split("(")[0]).split("::")[-1]
+        name = name.replace("void ", "").replace("_kernel", "").strip()
         vals = []
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = H.index(k)
