@@ -629,6 +629,10 @@ def gpu_arm(args):
                "whole_run": {"value": chain_steps_whole / t_whole, "seconds": t_whole,
                              "proposals": props_whole, "chain_steps": chain_steps_whole,
                              "batch_steps": bt.stream_steps},
+               # where the sampler's host thread spent the whole run: waiting for staged draws (feed),
+               # inside gi_hmcb_stream_advance (the device loop + its final sync), handling records
+               "host_seconds": {k: round(float(v), 4) for k, v in bt.stream_profile.items()},
+               "draw_workers": len(getattr(bt, "_ahead_workers", [])) or None, "host_cores": os.cpu_count(),
                "api": api}
     else:
         np.random.seed(HMC["seed"])

@@ -18,6 +18,11 @@
 //                         order (identical bits on every CTA), forms e and adds
 //                         e * row-strip -- read from SHARED memory, not from HBM -- to its accumulator;
 //                         the slot is then refilled with row i + 2.
+// Round 2: a row waiting for its d_j no longer occupies a ring slot.  One iteration after its forward
+// dot the strip is copied from shared memory into 28 registers per thread and the slot is handed
+// straight back to the TMA unit, so TWO to THREE rows (112 - 170 KB) are in flight per SM instead of
+// one (the ring used to hold row i, the two rows waiting for their hand-off, and a single landing
+// slot: DRAM at 62 % of peak, latency-exposed); the adjoint update reads the registers.
 // No atomics (a same-address counter would serialise 148 L2 atomics per row), no grid-wide barrier:
 // a CTA only ever waits for rows published two iterations earlier.  What was tried and measured
 // slower on B200 (4096 x 2^20, two-pass 9.5 ms, this kernel 6.8 ms): release/acquire flags instead of
@@ -82,10 +87,11 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
     // thread owns doubles {2 tid, 2 tid + 1} of the group's first 512 and of its second 512, so a
     // warp's 16-byte shared-memory loads cover 512 contiguous bytes (conflict free; 32 contiguous
     // bytes per thread would be 2-way bank conflicts -- 44 % of the wavefronts in the ncu capture)
-    double xv[kFU][4], ga[kFU][4];
+    double xv[kFU][4], ga[kFU][4], rr[kFU][4];  // rr: the strip of the row whose d_j arrives next iteration
 #pragma unroll
     for (int u = 0; u < kFU; ++u) {
         const int64_t o0 = 1024LL * u + 2 * tid, o1 = o0 + 512;
+        rr[u][0] = rr[u][1] = rr[u][2] = rr[u][3] = 0.0;
         xv[u][0] = xv[u][1] = xv[u][2] = xv[u][3] = 0.0;
         if (o0 < Wb) { xv[u][0] = __ldg(a.x + c0 + o0); xv[u][1] = __ldg(a.x + c0 + o0 + 1); }
         if (o1 < Wb) { xv[u][2] = __ldg(a.x + c0 + o1); xv[u][3] = __ldg(a.x + c0 + o1 + 1); }
@@ -131,14 +137,28 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
                      : "memory");
     };
     // Iteration i: forward dot of row i (published), then the adjoint update with row j = i - 2.
+    // Synchronisation inside the CTA (round 2): ONE full barrier per iteration.  The two hand-offs to
+    // thread 0 -- "all warps' dot partials are in scratch" (publish) and "all warps are done with the
+    // slot" (refill) -- are named barriers on which the other seven warps only ARRIVE, so they run on
+    // into the poll check / the next row while warp 0 publishes or re-arms the TMA.
     const double m0 = a.center ? a.mean_io[a.mean_slot] : 0.0;  // last evaluation's mean: e is formed around it, so
     double sd = 0.0;                           // the correction mean' * s below stays small
     unsigned long long pw0 = 0, pw1 = 0;       // prefetched words of the row consumed NEXT iteration
+    double *sA = scratch, *sV = scratch + 8;   // sA[8]: dot partials; sV[2][8]: d_j partials (by parity)
+    // strip bounds of this thread as group counts: o0 = 1024 u + 2 tid < Wb  <=>  u < n0 (second half: n1)
+    const int n0 = (int)max((int64_t)0, min((int64_t)kFU, (Wb - 2 * tid + 1023) / 1024));
+    const int n1 = (int)max((int64_t)0, min((int64_t)kFU, (Wb - 512 - 2 * tid + 1023) / 1024));
+    double nfix = 0.0, ndobs = 0.0;            // fix[j], dobs_c[j] of the row consumed NEXT iteration
+    if (a.nrows > 0 && kFLag == 1) { nfix = a.fix ? __ldg(a.fix) : 0.0; ndobs = __ldg(a.dobs_c); }
     for (int64_t i = 0; i < a.nrows + kFLag; ++i) {
         const int64_t j = i - kFLag;
         unsigned long long cw0 = pw0, cw1 = pw1;  // words of row j, polled during iteration i - 1
         if (tid < P && j + 1 >= 0 && j + 1 < a.nrows) poll(j + 1, pw0, pw1);
-        double acc = 0.0;
+        const double cfix = nfix, cdobs = ndobs;
+        if (j + 1 >= 0 && j + 1 < a.nrows) {      // off the critical path: an L2 round trip per row otherwise
+            nfix = a.fix ? __ldg(a.fix + j + 1) : 0.0;
+            ndobs = __ldg(a.dobs_c + j + 1);
+        }
         if (i < a.nrows) {
             // ---- phase 1: partial dot product of row i with this CTA's slice of x ------------
             const int slot = (int)(i % kFS);
@@ -151,79 +171,90 @@ __global__ void __launch_bounds__(kFT, 1) fused_pass_kernel(FusedArgs a) {
                     : "r"(bar), "r"(parity)
                     : "memory");
             const unsigned row_a = ring_a + (unsigned)(slot * W * 8) + 16u * tid;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four chains: the DFMA latency is not serialised 28 deep
 #pragma unroll
             for (int u = 0; u < kFU; ++u) {
-                const int64_t o0 = 1024LL * u + 2 * tid;
                 double g0, g1;
-                if (o0 < Wb) {
+                if (u < n0) {
                     lds2(row_a + 8192u * u, g0, g1);
-                    acc = fma(g0, xv[u][0], acc);
-                    acc = fma(g1, xv[u][1], acc);
+                    a0 = fma(g0, xv[u][0], a0);
+                    a1 = fma(g1, xv[u][1], a1);
                 }
-                if (o0 + 512 < Wb) {
+                if (u < n1) {
                     lds2(row_a + 8192u * u + 4096u, g0, g1);
-                    acc = fma(g0, xv[u][2], acc);
-                    acc = fma(g1, xv[u][3], acc);
+                    a2 = fma(g0, xv[u][2], a2);
+                    a3 = fma(g1, xv[u][3], a3);
                 }
             }
-        }
-        double v = 0.0;
-        if (j >= 0 && tid < P) {
-            // the complete row j: this thread's share is CTA `tid`'s partial
-            const unsigned long long target = (a.epoch_base + (unsigned long long)j + 1ull) & 0xffffffffull;
-            unsigned long long spins = 0;
-            while ((cw0 >> 32) != target || (cw1 >> 32) != target) {
-                poll(j, cw0, cw1);
-                if (++spins > kSpinLimit) __trap();
+            const double acc = warp_sum((a0 + a1) + (a2 + a3));
+            if (lane == 0) sA[warp] = acc;
+            if (warp == 0) {
+                asm volatile("barrier.cta.sync 1, %0;" ::"n"(kFT) : "memory");
+                if (tid == 0) {
+                    double t = 0.0;
+                    for (int w = 0; w < kFT / 32; ++w) t += sA[w];
+                    const unsigned long long tag = (a.epoch_base + (unsigned long long)i + 1ull) << 32;
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
+                    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(a.part + 2 * (i * P + b)),
+                                 "l"((bits & 0xffffffffull) | tag), "l"((bits >> 32) | tag)
+                                 : "memory");
+                }
+            } else {
+                asm volatile("barrier.cta.arrive 1, %0;" ::"n"(kFT) : "memory");
             }
-            v = __longlong_as_double((long long)((cw0 & 0xffffffffull) | (cw1 << 32)));
         }
-        // one block-wide reduction for both: acc -> this CTA's partial of row i (thread 0 publishes),
-        // v -> d_j in a fixed order (identical bits on every CTA)
-        acc = warp_sum(acc);
-        v = warp_sum(v);
-        if (lane == 0) { scratch[warp] = acc; scratch[8 + warp] = v; }  // (free since the last barrier)
-        __syncthreads();
-        if (tid == 0 && i < a.nrows) {
-            double t = 0.0;
-            for (int w = 0; w < kFT / 32; ++w) t += scratch[w];
-            const unsigned long long tag = (a.epoch_base + (unsigned long long)i + 1ull) << 32;
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
-            asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1,%2};" ::"l"(a.part + 2 * (i * P + b)),
-                         "l"((bits & 0xffffffffull) | tag), "l"((bits >> 32) | tag)
-                         : "memory");
-        }
+        double *sv = sV + 8 * (int)(i & 1);
         if (j >= 0) {
-            // ---- phase 2: add e_j * (row j strip, still in shared memory) to the accumulator ---
+            double v = 0.0;
+            if (tid < P) {
+                // the complete row j: this thread's share is CTA `tid`'s partial
+                const unsigned long long target = (a.epoch_base + (unsigned long long)j + 1ull) & 0xffffffffull;
+                unsigned long long spins = 0;
+                while ((cw0 >> 32) != target || (cw1 >> 32) != target) {
+                    poll(j, cw0, cw1);
+                    if (++spins > kSpinLimit) __trap();
+                }
+                v = __longlong_as_double((long long)((cw0 & 0xffffffffull) | (cw1 << 32)));
+            }
+            v = warp_sum(v);  // d_j in a fixed order (identical bits on every CTA)
+            if (lane == 0) sv[warp] = v;
+        }
+        __syncthreads();  // the one full barrier: d_j's partials are in, last iteration's reads of sv' are done
+        if (j >= 0) {
+            // ---- phase 2: add e_j * (row j strip, held in registers since last iteration) -------
             double dj = 0.0;
-            for (int w = 0; w < kFT / 32; ++w) dj += scratch[8 + w];
-            const double dinv = (a.fix ? dj + __ldg(a.fix + j) : dj) - m0;
-            const double ej = dinv - __ldg(a.dobs_c + j);
+            for (int w = 0; w < kFT / 32; ++w) dj += sv[w];
+            const double dinv = (a.fix ? dj + cfix : dj) - m0;
+            const double ej = dinv - cdobs;
             sd += dinv;
-            const unsigned row_a = ring_a + (unsigned)((int)(j % kFS) * W * 8) + 16u * tid;
 #pragma unroll
             for (int u = 0; u < kFU; ++u) {
-                const int64_t o0 = 1024LL * u + 2 * tid;
-                double g0, g1;
-                if (o0 < Wb) {
-                    lds2(row_a + 8192u * u, g0, g1);
-                    ga[u][0] = fma(g0, ej, ga[u][0]);
-                    ga[u][1] = fma(g1, ej, ga[u][1]);
-                }
-                if (o0 + 512 < Wb) {
-                    lds2(row_a + 8192u * u + 4096u, g0, g1);
-                    ga[u][2] = fma(g0, ej, ga[u][2]);
-                    ga[u][3] = fma(g1, ej, ga[u][3]);
-                }
+                ga[u][0] = fma(rr[u][0], ej, ga[u][0]);
+                ga[u][1] = fma(rr[u][1], ej, ga[u][1]);
+                ga[u][2] = fma(rr[u][2], ej, ga[u][2]);
+                ga[u][3] = fma(rr[u][3], ej, ga[u][3]);
             }
             if (tid == 0 && b == (int)(j % P)) a.d_out[j] = dj;
-            __syncthreads();  // every thread is done with slot j % kFS (and with scratch)
-            if (tid == 0 && j + kFS < a.nrows) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(j + kFS);
+        }
+        const int64_t k = i - 1;  // the row whose forward dot ran last iteration: shared memory -> registers
+        if (k >= 0 && k < a.nrows) {
+            const unsigned row_a = ring_a + (unsigned)((int)(k % kFS) * W * 8) + 16u * tid;
+#pragma unroll
+            for (int u = 0; u < kFU; ++u) {
+                if (u < n0) lds2(row_a + 8192u * u, rr[u][0], rr[u][1]);
+                if (u < n1) lds2(row_a + 8192u * u + 4096u, rr[u][2], rr[u][3]);
             }
-        } else {
-            __syncthreads();  // scratch is reused next iteration
+            // every warp is done with slot k % kFS: warp 0 hands it back to the TMA unit (one iteration
+            // after the row's dot), the others only arrive
+            if (warp == 0) {
+                asm volatile("barrier.cta.sync 2, %0;" ::"n"(kFT) : "memory");
+                if (tid == 0 && k + kFS < a.nrows) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(k + kFS);
+                }
+            } else {
+                asm volatile("barrier.cta.arrive 2, %0;" ::"n"(kFT) : "memory");
+            }
         }
     }
     // g = Aw^T e - mean' * s   (r = e - mean', mean' = mean - m0)

@@ -304,8 +304,10 @@ class _Stager(threading.Thread):
 
     SLOTS = _lib.STREAM_QUEUE_DEPTH + 2  # per chain: the handle's queue + two staged beyond it
 
-    def __init__(self, ring, nchains, M, dev):
+    def __init__(self, ring, nchains, M, dev, cols=None):
         super().__init__(daemon=True)
+        # peer-mode shards update their own column slice only: that is all of p0 this rank needs
+        self.cols = (0, M) if cols is None else (int(cols[0]), int(cols[1]))
         import queue
 
         torch = _lib.require_cuda()
@@ -339,11 +341,13 @@ class _Stager(threading.Thread):
                     ring.wait_ready(c, k)
                     row = ring.data[c, k % ring.depth]
                     L, u = int(row[M]), float(row[M + 1])
-                    buf.copy_(ring.tdata[c, k % ring.depth], non_blocking=True)
+                    lo, hi = self.cols
+                    if hi > lo:
+                        buf[lo:hi].copy_(ring.tdata[c, k % ring.depth][lo:hi], non_blocking=True)
                     landed.record(side)
                     landed.synchronize()  # the side stream only, without spinning
                     ring.release(c, k)
-                    self.bytes_h2d += 8 * (M + 2)
+                    self.bytes_h2d += 8 * (hi - lo) + 16
                     with self.cv:
                         self.ready[c].append((L, u, buf[:M]))
                         self.cv.notify_all()
@@ -654,6 +658,7 @@ class HMCBatch:
             nw = max(1, int(os.environ["GI_DRAW_WORKERS"]))
         self._ahead = _DrawAhead(self.streams, self.Lrange, M, self.Sigma, ring, nworkers=nw, owned=owned)
         self._ahead.limit = limit
+        self._ahead_workers = self._ahead.workers
         self._ahead.start()
         self._stream_buffers()
         if wait:
@@ -700,7 +705,12 @@ class HMCBatch:
         self._ahead = None
         if max_proposals is not None:
             ahead.limit = max_proposals if ahead.limit is None else min(ahead.limit, max_proposals)
-        stager = _Stager(ahead.ring, nc, M, self.model.Aw_pad.device)
+        cols = None
+        if self._peer is not None:
+            lo_c, hi_c = C.c_int64(), C.c_int64()
+            _lib.check(lib.gi_hmcb_owned_columns(self._h, C.byref(lo_c), C.byref(hi_c)), "gi_hmcb_owned_columns")
+            cols = (lo_c.value, hi_c.value)
+        stager = _Stager(ahead.ring, nc, M, self.model.Aw_pad.device, cols)
         stager.start()
         requested, finished = [0] * nc, [0] * nc
         depth = _lib.STREAM_QUEUE_DEPTH
