@@ -590,7 +590,9 @@ def gpu_arm(args):
         # drain included) and the steady-state window that opens when the first proposal of the batch
         # has finished and closes when the first chain has completed its quota.
         nprop = max(args.e2e_proposals, int(round(args.steps / 12.5)) + 2)
-        bt.advance_cap = 4  # records (and the window's clock) come back every <= 4 batch steps
+        # records (and the window's clock) come back every <= 16 batch steps: every call drains the device
+        # queue (the host reads the records back), which at 16 ms per step (8 GPUs) costs ~3 ms per call
+        bt.advance_cap = 16
         bt.proposals = [[] for _ in range(nch)]
         window = {}
 

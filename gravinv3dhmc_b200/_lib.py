@@ -124,6 +124,7 @@ SIGNATURES = {
     "gi_peer_destroy": (C.c_int, [_P]),
     "gi_peer_bytes_sent": (_I64, [_P]),
     "gi_peer_allreduce_small": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "gi_peer_columns": (C.c_int, [_I64, C.c_int32, _P]),
     "gi_hmcb_peer_bytes": (_I64, [_P, C.c_int32]),
     "gi_hmcb_set_peer": (C.c_int, [_P, _P, _I64, _P]),
     "gi_hmcb_owned_columns": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),

@@ -1307,6 +1307,13 @@ static int64_t peer_pitch(int64_t ld, int world) {
     return std::max<int64_t>(w, 4);
 }
 
+// host-only: the column slices of a peer-mode batch, col[0..world] (slice q = [col[q], col[q+1]))
+extern "C" int gi_peer_columns(int64_t ld, int32_t world, int64_t *col) {
+    GI_REQUIRE(col && ld > 0 && world >= 1 && world <= kPeerMax, "gi_peer_columns: bad argument");
+    peer_columns(ld, world, col);
+    return GI_OK;
+}
+
 extern "C" int64_t gi_hmcb_peer_bytes(const gi_hmcb *h, int32_t world) {
     if (!h || world < 1 || world > kPeerMax) return -1;
     const bool logc = h->cfg.reg.constraint == GI_CONSTRAINT_LOGARITHMIC;

@@ -384,6 +384,9 @@ int64_t gi_peer_bytes_sent(const gi_peer *p);
 /* in-place sum over the ranks of n doubles (8..512, a multiple of 8) on the device, identical bits on
  * every rank: the scalar exchange above, exposed for set-up reductions and tests */
 int gi_peer_allreduce_small(gi_peer *p, double *vec_dev, int32_t n, void *stream);
+/* host-only helper: the column slices, col[0..world]; slice q = [col[q], col[q+1]) is a whole number of
+ * the adjoint kernel's 256-column strips (the last one ends at ld) and may be empty */
+int gi_peer_columns(int64_t ld, int32_t world, int64_t *col);
 int64_t gi_hmcb_peer_bytes(const gi_hmcb *h, int32_t world);
 int gi_hmcb_set_peer(gi_hmcb *h, gi_peer *peer, int64_t n_total, const double *dobs_c_host);
 int gi_hmcb_owned_columns(const gi_hmcb *h, int64_t *lo, int64_t *hi);
