@@ -134,6 +134,10 @@ SIGNATURES = {
     "gi_hmcb_stream_runway": (C.c_int, [_P, C.POINTER(C.c_int32)]),
     "gi_hmcb_stream_advance": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), _P]),
+    "gi_hmcb_stream_advance_begin": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "gi_hmcb_stream_advance_end": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "gi_hmcb_stream_queue_space": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    "gi_hmcb_stream_cancel": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     "gi_hmcb_leapfrog_steps": (C.c_int, [_P, _P, C.c_int32, _D]),
     "gi_hmcb_launch_count": (_I64, [_P]),
     "gi_hmcb_padded_chains": (C.c_int32, [_P]),

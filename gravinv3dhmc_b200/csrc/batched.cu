@@ -998,6 +998,8 @@ struct gi_hmcb {
     cudaStream_t push_stream;
     cudaEvent_t ev_upd, ev_push;
     bool push_pending;
+    bool adv_pending;      // gi_hmcb_stream_advance_begin was called, its records are still on the device
+    int adv_nrec, adv_done;
     double *own_xa, *own_xb, *own_mwa, *own_mwb;  // the handle's own buffers, replaced by symmetric ones
     int64_t peer_steps;
 };
@@ -1652,6 +1654,7 @@ extern "C" int gi_hmcb_stream_begin(gi_hmcb *h, double dt) {
         GI_CUDA(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
     }
     h->copies_pending = false;
+    h->adv_pending = false;
     memset(h->cq, 0, sizeof(h->cq));
     h->streaming = true;
     h->stream_dt = dt;
@@ -1731,12 +1734,12 @@ static int launch_update_modes(gi_hmcb *h, const double *grad_in, const double *
     return GI_OK;
 }
 
-extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records,
-                                      int32_t max_records, int32_t *nrecords, int32_t *steps_done,
-                                      double *x_host) {
-    GI_REQUIRE(h && h->streaming && nrecords, "gi_hmcb_stream_advance: not streaming");
-    GI_REQUIRE(nsteps >= 0 && max_records >= 0 && (records || max_records == 0),
-               "gi_hmcb_stream_advance: bad argument");
+// queue the kernels of up to nsteps batch steps; the finished proposals' records stay on the device
+// until stream_collect
+static int stream_enqueue(gi_hmcb *h, int32_t nsteps, int32_t max_records, double *x_host) {
+    GI_REQUIRE(h && h->streaming, "gi_hmcb_stream_advance: not streaming");
+    GI_REQUIRE(nsteps >= 0 && max_records >= 0, "gi_hmcb_stream_advance: bad argument");
+    GI_REQUIRE(!h->adv_pending, "gi_hmcb_stream_advance: the previous call's records were not collected");
     cudaStream_t s = h->stream;
     const int64_t M = h->cfg.M, ld = h->cfg.ld, N = h->cfg.N;
     const int C = (int)h->C;
@@ -1860,6 +1863,20 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
         else { h->s_mwin = h->s_xin; h->s_mwout = h->s_xout; }
         if (any_active) done += 1;
     }
+    h->adv_pending = true;
+    h->adv_nrec = nrec;
+    h->adv_done = done;
+    return GI_OK;
+}
+
+// wait for the queued steps and hand out their records
+static int stream_collect(gi_hmcb *h, gi_stream_record *records, int32_t max_records, int32_t *nrecords,
+                          int32_t *steps_done) {
+    GI_REQUIRE(h && h->streaming && nrecords && h->adv_pending, "gi_hmcb_stream_advance_end: nothing pending");
+    cudaStream_t s = h->stream;
+    const int nrec = h->adv_nrec, done = h->adv_done;
+    GI_REQUIRE(nrec <= max_records && (records || nrec == 0), "gi_hmcb_stream_advance_end: record buffer too small");
+    h->adv_pending = false;
     if (nrec > 0) {
         // device fields (accept, U, H) come back through a staging copy, host fields are kept
         gi_stream_record *tmp = new gi_stream_record[nrec];
@@ -1882,6 +1899,40 @@ extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_reco
     }
     *nrecords = nrec;
     if (steps_done) *steps_done = done;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records,
+                                      int32_t max_records, int32_t *nrecords, int32_t *steps_done,
+                                      double *x_host) {
+    GI_REQUIRE(nrecords && (records || max_records == 0), "gi_hmcb_stream_advance: bad argument");
+    int rc = stream_enqueue(h, nsteps, max_records, x_host);
+    if (rc) return rc;
+    return stream_collect(h, records, max_records, nrecords, steps_done);
+}
+
+extern "C" int gi_hmcb_stream_advance_begin(gi_hmcb *h, int32_t nsteps, int32_t max_records, double *x_host) {
+    return stream_enqueue(h, nsteps, max_records, x_host);
+}
+
+extern "C" int gi_hmcb_stream_advance_end(gi_hmcb *h, gi_stream_record *records, int32_t max_records,
+                                          int32_t *nrecords, int32_t *steps_done) {
+    return stream_collect(h, records, max_records, nrecords, steps_done);
+}
+
+// drop the proposals queued for `chain` that have not started (the chain has all the samples it needs)
+extern "C" int gi_hmcb_stream_cancel(gi_hmcb *h, int32_t chain, int32_t *dropped) {
+    GI_REQUIRE(h && h->streaming && chain >= 0 && chain < h->nchains, "gi_hmcb_stream_cancel: bad argument");
+    GI_REQUIRE(!h->adv_pending, "gi_hmcb_stream_cancel: collect the pending records first");
+    if (dropped) *dropped = h->cq[chain].qn;
+    h->cq[chain].qn = 0;
+    return GI_OK;
+}
+
+extern "C" int gi_hmcb_stream_queue_space(gi_hmcb *h, int32_t chain, int32_t *space) {
+    GI_REQUIRE(h && h->streaming && space && chain >= 0 && chain < h->nchains,
+               "gi_hmcb_stream_queue_space: bad argument");
+    *space = GI_STREAM_QUEUE_DEPTH - h->cq[chain].qn;
     return GI_OK;
 }
 

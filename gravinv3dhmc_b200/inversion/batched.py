@@ -364,6 +364,15 @@ class _Stager(threading.Thread):
                 self.cv.wait(0.05)
             return self.ready[c].popleft()
 
+    def try_take(self, c):
+        """like take(), but None when the chain's next draw is not staged yet"""
+        with self.cv:
+            if self.ready[c]:
+                return self.ready[c].popleft()
+            if self.error is not None:
+                raise RuntimeError("draw stager failed") from self.error
+            return None
+
     def stop(self):
         self.req.put(None)
 
@@ -699,7 +708,7 @@ class HMCBatch:
         keep_x = write or on_record is not None or self.sink is None
         cap = len(recs)
         nrec, ndone = C.c_int32(), C.c_int32()
-        count, fed, inflight = [0] * nc, [0] * nc, [0] * nc
+        count, fed, inflight, cancelled = [0] * nc, [0] * nc, [0] * nc, [False] * nc
         live = [True] * nc           # still needs accepted samples
         ahead = self._ahead or self.start_draws(limit=max_proposals)
         self._ahead = None
@@ -731,28 +740,46 @@ class HMCBatch:
                     stager.request(c)
                     requested[c] += 1
         _lib.check(lib.gi_hmcb_stream_begin(self._h, float(self.dt)), "gi_hmcb_stream_begin")
+        space = C.c_int32()
+
+        def feed(block):
+            """hand staged draws to every live chain whose device queue has room; `block`: wait for a
+            draw that is not staged yet (needed for progress before a call, not in a call's shadow)"""
+            for c in range(nc):
+                while live[c] and (max_proposals is None or fed[c] < max_proposals):
+                    _lib.check(lib.gi_hmcb_stream_queue_space(self._h, c, C.byref(space)),
+                               "gi_hmcb_stream_queue_space")
+                    if space.value <= 0:
+                        break
+                    item = stager.take(c) if block else stager.try_take(c)
+                    if item is None:
+                        break
+                    L, u, p0d = item  # staged on the device by the side stream
+                    _lib.check(lib.gi_hmcb_stream_feed_dev(self._h, c, L, u, _lib.ptr(p0d)),
+                               "gi_hmcb_stream_feed_dev")
+                    inflight[c] += 1
+                    fed[c] += 1
+
         self.stream_steps = 0
         import time as _time
         prof = self.stream_profile = dict(feed=0.0, advance=0.0, records=0.0, calls=0)
         try:
             while True:
                 _t0 = _time.perf_counter()
-                for c in range(nc):
-                    while live[c] and inflight[c] < depth and (max_proposals is None or fed[c] < max_proposals):
-                        L, u, p0d = stager.take(c)  # staged on the device by the side stream
-                        _lib.check(lib.gi_hmcb_stream_feed_dev(self._h, c, L, u, _lib.ptr(p0d)),
-                                   "gi_hmcb_stream_feed_dev")
-                        inflight[c] += 1
-                        fed[c] += 1
+                feed(True)
                 run = C.c_int32()
                 _lib.check(lib.gi_hmcb_stream_runway(self._h, C.byref(run)), "gi_hmcb_stream_runway")
                 if run.value == 0:
                     break
                 _t1 = _time.perf_counter()
                 nrun = run.value if self.advance_cap is None else min(run.value, int(self.advance_cap))
-                _lib.check(lib.gi_hmcb_stream_advance(self._h, nrun, recs, cap, C.byref(nrec),
-                                                      C.byref(ndone), _lib.ptr(xh) if keep_x else None),
-                           "gi_hmcb_stream_advance")
+                # queue the device work, then -- in its shadow -- feed the queue slots the scheduled steps
+                # free (the schedule is deterministic: it does not wait for the Metropolis outcomes)
+                _lib.check(lib.gi_hmcb_stream_advance_begin(self._h, nrun, cap, _lib.ptr(xh) if keep_x else None),
+                           "gi_hmcb_stream_advance_begin")
+                feed(False)
+                _lib.check(lib.gi_hmcb_stream_advance_end(self._h, recs, cap, C.byref(nrec), C.byref(ndone)),
+                           "gi_hmcb_stream_advance_end")
                 self.stream_steps += ndone.value
                 _t2 = _time.perf_counter()
                 prof["feed"] += _t1 - _t0
@@ -795,6 +822,12 @@ class HMCBatch:
                         sys.stdout.flush()
                     if max_proposals is not None and len(self.proposals[c]) >= max_proposals:
                         live[c] = False
+                for c in range(nc):
+                    if not live[c] and inflight[c] > 0 and not cancelled[c]:
+                        # the chain has its samples: what is still queued for it would only be thrown away
+                        _lib.check(lib.gi_hmcb_stream_cancel(self._h, c, C.byref(space)), "gi_hmcb_stream_cancel")
+                        inflight[c] -= space.value
+                        cancelled[c] = True
                 prof["records"] += _time.perf_counter() - _t2
         finally:
             # the stager finishes the requests already queued (the same sequence on every rank, so

@@ -417,6 +417,18 @@ int gi_hmcb_stream_feed_dev(gi_hmcb *h, int32_t chain, int32_t L, double u, cons
 int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps);
 int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records, int32_t max_records,
                            int32_t *nrecords, int32_t *steps_done, double *x_host);
+/* advance in two halves: _begin queues the kernels of up to nsteps batch steps and returns at once (the
+ * schedule does not depend on the Metropolis outcomes), _end waits for them and hands out the records.
+ * Between the two the host may feed the queue slots the scheduled steps have freed
+ * (gi_hmcb_stream_queue_space), so that drawing and staging the next proposals overlaps the device work
+ * instead of leaving the device idle between calls. */
+int gi_hmcb_stream_advance_begin(gi_hmcb *h, int32_t nsteps, int32_t max_records, double *x_host);
+int gi_hmcb_stream_advance_end(gi_hmcb *h, gi_stream_record *records, int32_t max_records,
+                               int32_t *nrecords, int32_t *steps_done);
+int gi_hmcb_stream_queue_space(gi_hmcb *h, int32_t chain, int32_t *space);
+/* drop the queued, not yet started proposals of `chain` (it has reached its sample count); the one in
+ * flight still finishes and is recorded */
+int gi_hmcb_stream_cancel(gi_hmcb *h, int32_t chain, int32_t *dropped);
 /* benchmark helper: nsteps leapfrog steps of every chain, no Metropolis; p0_dev is [Cp][ld] or NULL */
 int gi_hmcb_leapfrog_steps(gi_hmcb *h, const double *p0_dev, int32_t nsteps, double dt);
 int64_t gi_hmcb_launch_count(const gi_hmcb *h);
