@@ -41,7 +41,11 @@ WORKLOADS = {
     "mid": ((32, 64, 64), 100.0, 64),         # 131 072 voxels x 4096 obs (4.3 GB)
     "tiny": ((16, 32, 32), 100.0, 32),        # 16 384 voxels x 1024 obs
 }
-HMC = dict(delta=0.01, Sigma=0.001, Lrange=[5, 20], RegulFactor=1.0, regularization="Damping",
+# delta: SURVEY.md 8(d) suggests 0.01 (the value of the 600-observation examples); with 16 384
+# observations that step is beyond the leapfrog's stability limit (the stiffest direction of Aw^T Aw
+# grows with the row count) and EVERY proposal is rejected -- measured in round 2.  0.003 accepts ~85 %
+# of the proposals (gpurun_out/r02_accept_scan.log -> profiles/); the work per step is the same.
+HMC = dict(delta=0.003, Sigma=0.001, Lrange=[5, 20], RegulFactor=1.0, regularization="Damping",
            beta=0.001, rhomin=0.0, rhomax=1.0, init=0.001, seed=100)
 
 
@@ -597,14 +601,13 @@ def gpu_arm(args):
         window = {}
 
         def on_record(c, r, acc):
+            # records are handled one call late, in the shadow of the next call: the window is cut at the
+            # END of the call they belong to (bt.stream_mark = host time and batch steps at that point)
+            tm, st, nr = bt.stream_mark
             if "t0" not in window:
-                torch.cuda.synchronize()
-                window.update(t0=time.perf_counter(), s0=bt.stream_steps,
-                              p0=sum(len(q) for q in bt.proposals))
+                window.update(t0=tm, s0=st, p0=nr)
             if "t" not in window and len(bt.proposals[c]) >= nprop:
-                torch.cuda.synchronize()
-                window.update(t=time.perf_counter() - window["t0"], steps=bt.stream_steps - window["s0"],
-                              props=sum(len(q) for q in bt.proposals) - window["p0"])
+                window.update(t=tm - window["t0"], steps=st - window["s0"], props=nr - window["p0"])
 
         bt.stream(10 ** 9, 0, max_proposals=nprop, write=False, on_record=on_record)
         torch.cuda.synchronize()
@@ -628,12 +631,15 @@ def gpu_arm(args):
                "h2d_bytes_per_step": int(nprops_done * (8 * M + 12) / steps_done),
                "d2h_bytes_per_step": int(nprops_done * (8 * M + 80) / steps_done),
                "proposals": nprops_done, "window_seconds": t_e2e,
+               "accepted_whole_run": int(sum(1 for q in bt.proposals for _, a in q if a)),
                "whole_run": {"value": chain_steps_whole / t_whole, "seconds": t_whole,
                              "proposals": props_whole, "chain_steps": chain_steps_whole,
                              "batch_steps": bt.stream_steps},
                # where the sampler's host thread spent the whole run: waiting for staged draws (feed),
                # inside gi_hmcb_stream_advance (the device loop + its final sync), handling records
                "host_seconds": {k: round(float(v), 4) for k, v in bt.stream_profile.items()},
+               # per call of the device loop: [batch steps, records, ms feeding before it, ms per batch step in it]
+               "calls": [[n, r, round(1e3 * f, 2), round(1e3 * a / max(n, 1), 3)] for n, r, f, a in bt.stream_calls],
                "draw_workers": len(getattr(bt, "_ahead_workers", [])) or None, "host_cores": os.cpu_count(),
                "api": api}
     else:

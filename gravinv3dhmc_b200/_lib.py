@@ -132,6 +132,7 @@ SIGNATURES = {
     "gi_hmcb_stream_feed": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _P]),
     "gi_hmcb_stream_feed_dev": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _P]),
     "gi_hmcb_stream_runway": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "gi_hmcb_stream_close_chain": (C.c_int, [_P, C.c_int32]),
     "gi_hmcb_stream_advance": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32), _P]),
     "gi_hmcb_stream_advance_begin": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),

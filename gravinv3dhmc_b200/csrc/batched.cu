@@ -966,6 +966,7 @@ struct gi_hmcb {
     // streaming sampler
     struct ChainQ {
         int L_cur, pos, qn, qhead;
+        int closed;  // the host has no more proposals for this chain: it may run dry (runway ignores it)
         int qL[GI_STREAM_QUEUE_DEPTH];
         double qu[GI_STREAM_QUEUE_DEPTH];
         int64_t seq;
@@ -1693,15 +1694,26 @@ extern "C" int gi_hmcb_stream_feed_dev(gi_hmcb *h, int32_t chain, int32_t L, dou
 
 extern "C" int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps) {
     GI_REQUIRE(h && h->streaming && steps, "gi_hmcb_stream_runway: not streaming");
-    int best = -1;
+    // steps until a chain the host still has proposals for would run dry; closed chains are allowed to
+    // (they park), so they only count when nothing else is left
+    int best = -1, longest = 0;
     for (int c = 0; c < h->nchains; ++c) {
         const gi_hmcb::ChainQ &q = h->cq[c];
         if (q.L_cur == 0 && q.qn == 0) continue;  // parked chain
         int rem = q.L_cur > 0 ? q.L_cur - q.pos : 0;
         for (int k = 0; k < q.qn; ++k) rem += q.qL[(q.qhead + k) % GI_STREAM_QUEUE_DEPTH];
+        longest = std::max(longest, rem);
+        if (q.closed) continue;
         if (best < 0 || rem < best) best = rem;
     }
-    *steps = best < 0 ? 0 : best;
+    *steps = best < 0 ? longest : best;
+    return GI_OK;
+}
+
+// the host has fed the last proposal of `chain`: the chain may run dry without ending a call early
+extern "C" int gi_hmcb_stream_close_chain(gi_hmcb *h, int32_t chain) {
+    GI_REQUIRE(h && h->streaming && chain >= 0 && chain < h->nchains, "gi_hmcb_stream_close_chain: bad argument");
+    h->cq[chain].closed = 1;
     return GI_OK;
 }
 
@@ -1820,18 +1832,7 @@ static int stream_enqueue(gi_hmcb *h, int32_t nsteps, int32_t max_records, doubl
                 if (rc) return rc;
                 h->launches += 2;
             }
-            if (x_host) {
-                // the copies run on their own stream, under the next steps' contractions
-                GI_CUDA(cudaEventRecord(h->ev_commit, s));
-                GI_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_commit, 0));
-                for (int c = 0; c < h->nchains; ++c)
-                    if (sc.fin[c])
-                        GI_CUDA(cudaMemcpyAsync(x_host + (int64_t)sc.rec[c] * M, h->x_cur + c * ld,
-                                                sizeof(double) * M, cudaMemcpyDeviceToHost,
-                                                h->copy_stream));
-                GI_CUDA(cudaEventRecord(h->ev_copied, h->copy_stream));
-                h->copies_pending = true;
-            }
+            if (x_host) GI_CUDA(cudaEventRecord(h->ev_commit, s));
         }
         if (any_start) {
             // opening half step of the next trajectory from the (possibly just committed) state
@@ -1847,6 +1848,20 @@ static int stream_enqueue(gi_hmcb *h, int32_t nsteps, int32_t max_records, doubl
         // the next step's forward pass)
         rc = hb_push(h, h->s_xout, h->s_mwout);
         if (rc) return rc;
+        if (any_fin && x_host) {
+            // the finished chains' positions go to the host on their own stream, under the next steps'
+            // contractions -- and, in peer mode, BEHIND this step's slice pushes: both are copy-engine
+            // work, and a 40 MB PCIe read queued ahead of the NVLink pushes would hold back every
+            // peer's forward pass (measured: 1.5 ms per step at 8 GPUs)
+            GI_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_commit, 0));
+            if (h->peer && h->push_pending) GI_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_push, 0));
+            for (int c = 0; c < h->nchains; ++c)
+                if (sc.fin[c])
+                    GI_CUDA(cudaMemcpyAsync(x_host + (int64_t)sc.rec[c] * M, h->x_cur + c * ld,
+                                            sizeof(double) * M, cudaMemcpyDeviceToHost, h->copy_stream));
+            GI_CUDA(cudaEventRecord(h->ev_copied, h->copy_stream));
+            h->copies_pending = true;
+        }
         for (int c = 0; c < h->nchains; ++c) {
             gi_hmcb::ChainQ &q = h->cq[c];
             if (modeA[c] == 0) q.pos += 1;

@@ -707,8 +707,9 @@ class HMCBatch:
         # output "none": the accepted positions stay on the device (the sink, if any, has them)
         keep_x = write or on_record is not None or self.sink is None
         cap = len(recs)
+        mirror = keep_x and write  # keep self.x current per record (else it is read back once at the end)
         nrec, ndone = C.c_int32(), C.c_int32()
-        count, fed, inflight, cancelled = [0] * nc, [0] * nc, [0] * nc, [False] * nc
+        count, fed, inflight, cancelled, closed = [0] * nc, [0] * nc, [0] * nc, [False] * nc, [False] * nc
         live = [True] * nc           # still needs accepted samples
         ahead = self._ahead or self.start_draws(limit=max_proposals)
         self._ahead = None
@@ -746,6 +747,11 @@ class HMCBatch:
             """hand staged draws to every live chain whose device queue has room; `block`: wait for a
             draw that is not staged yet (needed for progress before a call, not in a call's shadow)"""
             for c in range(nc):
+                if not closed[c] and (not live[c] or (max_proposals is not None and fed[c] >= max_proposals)):
+                    # nothing more will be fed to this chain: it may run dry without ending a call early
+                    # (fed / live are the same on every rank, so the calls stay aligned across ranks)
+                    _lib.check(lib.gi_hmcb_stream_close_chain(self._h, c), "gi_hmcb_stream_close_chain")
+                    closed[c] = True
                 while live[c] and (max_proposals is None or fed[c] < max_proposals):
                     _lib.check(lib.gi_hmcb_stream_queue_space(self._h, c, C.byref(space)),
                                "gi_hmcb_stream_queue_space")
@@ -763,6 +769,9 @@ class HMCBatch:
         self.stream_steps = 0
         import time as _time
         prof = self.stream_profile = dict(feed=0.0, advance=0.0, records=0.0, calls=0)
+        self.stream_calls = []  # per call: (batch steps, records, seconds feeding before it, seconds in it)
+        self.stream_mark = (0.0, 0, 0)  # (host time, batch steps, records) at the end of the call being handled
+        nrec_total = 0
         try:
             while True:
                 _t0 = _time.perf_counter()
@@ -782,6 +791,9 @@ class HMCBatch:
                            "gi_hmcb_stream_advance_end")
                 self.stream_steps += ndone.value
                 _t2 = _time.perf_counter()
+                nrec_total += int(nrec.value)
+                self.stream_mark = (_t2, self.stream_steps, nrec_total)
+                self.stream_calls.append((int(ndone.value), int(nrec.value), _t1 - _t0, _t2 - _t1))
                 prof["feed"] += _t1 - _t0
                 prof["advance"] += _t2 - _t1
                 prof["calls"] += 1
@@ -798,7 +810,7 @@ class HMCBatch:
                     Udn, Umn = r.U_data / data_size, r.U_model / model_size
                     Un = Udn + alpha * Umn
                     if acc:
-                        if keep_x:
+                        if mirror:  # (an 8 MB host copy per accepted sample at c5: only when it is written)
                             self.x[c] = xh[i].numpy()
                         if count[c] >= ndraws and write:
                             x = self.x[c]
@@ -840,7 +852,7 @@ class HMCBatch:
 
                 dist.barrier(group=self.model.group)  # nobody unmaps while another rank still reads
             ahead.ring.close()
-        if not keep_x:  # the device's current positions, once (a chain may have run a queued
+        if not mirror:  # the device's current positions, once (a chain may have run a queued
             # proposal past its target; the recorded statistics are gated and unaffected)
             _lib.check(lib.gi_hmcb_get_state(self._h, _lib.ptr(self.x), None, None), "gi_hmcb_get_state")
         return self.x

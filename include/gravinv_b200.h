@@ -415,6 +415,8 @@ int gi_hmcb_stream_feed(gi_hmcb *h, int32_t chain, int32_t L, double u, const do
 /* same as feed with the momentum draw already on the device (e.g. received by a broadcast) */
 int gi_hmcb_stream_feed_dev(gi_hmcb *h, int32_t chain, int32_t L, double u, const double *p0_dev);
 int gi_hmcb_stream_runway(gi_hmcb *h, int32_t *steps);
+/* the host has fed the last proposal of `chain`: runway no longer stops where this chain runs dry */
+int gi_hmcb_stream_close_chain(gi_hmcb *h, int32_t chain);
 int gi_hmcb_stream_advance(gi_hmcb *h, int32_t nsteps, gi_stream_record *records, int32_t max_records,
                            int32_t *nrecords, int32_t *steps_done, double *x_host);
 /* advance in two halves: _begin queues the kernels of up to nsteps batch steps and returns at once (the
