@@ -302,7 +302,11 @@ class _Stager(threading.Thread):
     copy on its own stream: the host-side exchange and the host->device transfer overlap the
     contractions already queued."""
 
-    SLOTS = _lib.STREAM_QUEUE_DEPTH + 2  # per chain: the handle's queue + two staged beyond it
+    # per chain: the handle's queue + four staged beyond it.  A call of 16 batch steps finishes up to three
+    # proposals per chain and their successors are requested all at once when its records come back; with
+    # only two staged beyond the queue the sampler waited ~20 ms per call for that burst to be staged
+    # (0.25 ms per draw, one stager thread) -- 1.1 ms per 16 ms batch step at 8 GPUs (measured, round 2)
+    SLOTS = _lib.STREAM_QUEUE_DEPTH + 4
 
     def __init__(self, ring, nchains, M, dev, cols=None):
         super().__init__(daemon=True)

@@ -7,3 +7,4 @@ echo "rc=$?" >> gpurun_out/r02l_tests.log
 ( time GI_CHECK_TIMEOUT=90 timeout 110 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py ) > gpurun_out/r02l_multi2.log 2>&1
 echo "rc=$?" >> gpurun_out/r02l_multi2.log
 tail -n 3 gpurun_out/r02l_tests.log; grep "multi_gpu_check\|rc=" gpurun_out/r02l_multi2.log
+bash tools/gpu_jobs/r02_n.sh
