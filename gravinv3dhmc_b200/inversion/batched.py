@@ -761,7 +761,17 @@ class HMCBatch:
                                "gi_hmcb_stream_queue_space")
                     if space.value <= 0:
                         break
-                    item = stager.take(c) if block else stager.try_take(c)
+                    if block:
+                        _tw = _time.perf_counter()
+                        item = stager.take(c)
+                        _tw = _time.perf_counter() - _tw
+                        prof["fed_before_call"] += 1
+                        if _tw > 1e-4:  # the draw was not staged yet: the device idles meanwhile
+                            prof["waits"] += 1
+                            prof["wait_seconds"] += _tw
+                    else:
+                        item = stager.try_take(c)
+                        prof["fed_in_shadow"] += item is not None
                     if item is None:
                         break
                     L, u, p0d = item  # staged on the device by the side stream
@@ -772,7 +782,8 @@ class HMCBatch:
 
         self.stream_steps = 0
         import time as _time
-        prof = self.stream_profile = dict(feed=0.0, advance=0.0, records=0.0, calls=0)
+        prof = self.stream_profile = dict(feed=0.0, advance=0.0, records=0.0, calls=0, fed_before_call=0,
+                                          fed_in_shadow=0, waits=0, wait_seconds=0.0)
         self.stream_calls = []  # per call: (batch steps, records, seconds feeding before it, seconds in it)
         self.stream_mark = (0.0, 0, 0)  # (host time, batch steps, records) at the end of the call being handled
         nrec_total = 0
