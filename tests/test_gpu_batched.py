@@ -277,3 +277,45 @@ def test_shard_hook_machinery_single_rank(tmp_path, npieces):
         bt.close()
     assert out["device"][0] == out["device-hooks"][0]
     assert np.allclose(out["device"][1], out["device-hooks"][1], rtol=1e-10, atol=1e-14)
+
+
+def test_mid_size_contractions_use_the_production_tiling():
+    """bench.py's `mid` shape (4096 observations x 131 072 voxels, 64 chains): large enough for the
+    production tile chooser -- whole waves of 148 CTAs, several k-chunks, 512 adjoint strips -- so the
+    tiling the c5 runs use is exercised under pytest, against a torch FP64 product
+    on sampled rows / columns and the linearity of both passes."""
+    L = _lib.lib()
+    n, m, nch = 4096, 131072, 64
+    ld = _lib.padded_ld(m)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(42)
+    A = torch.randn((n, ld), generator=gen, **f64)
+    plan = C.c_void_p()
+    _lib.check(L.gi_plan_create(n, m, ld, nch, C.byref(plan)))
+    cp, npad = C.c_int32(), C.c_int64()
+    _lib.check(L.gi_plan_batch_info(plan, C.byref(cp), C.byref(npad)))
+    assert cp.value == 64 and npad.value == n
+    X = torch.randn((cp.value, ld), generator=gen, **f64)
+    R = torch.randn((cp.value, npad.value), generator=gen, **f64)
+    D = torch.zeros((cp.value, n), **f64)
+    G = torch.zeros((cp.value, ld), **f64)
+    s = _lib.stream_ptr()
+    _lib.check(L.gi_gemm_fwd(plan, _lib.ptr(A), _lib.ptr(X), _lib.ptr(D), s))
+    _lib.check(L.gi_gemm_adj(plan, _lib.ptr(A), _lib.ptr(R), _lib.ptr(G), s))
+    rows = torch.tensor([0, 1, 127, 128, 2047, 2048, 4094, 4095], device="cuda")
+    ref = X @ A[rows].T
+    assert float((D[:, rows] - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    cols = torch.unique(torch.cat([torch.linspace(0, m - 1, 48, device="cuda").long(),
+                                   torch.tensor([0, 255, 256, 65535, 65536, m - 257, m - 256, m - 1], device="cuda")]))
+    ref = R @ A[:, cols]
+    assert float((G[:, cols] - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    # deterministic and linear: a second run gives the same bits, doubling the input doubles the output
+    D2, G2 = torch.zeros_like(D), torch.zeros_like(G)
+    _lib.check(L.gi_gemm_fwd(plan, _lib.ptr(A), _lib.ptr(X), _lib.ptr(D2), s))
+    _lib.check(L.gi_gemm_adj(plan, _lib.ptr(A), _lib.ptr(R), _lib.ptr(G2), s))
+    assert torch.equal(D, D2) and torch.equal(G, G2)
+    X.mul_(2.0)
+    _lib.check(L.gi_gemm_fwd(plan, _lib.ptr(A), _lib.ptr(X), _lib.ptr(D2), s))
+    assert torch.equal(D2, 2.0 * D)
+    L.gi_plan_destroy(plan)
