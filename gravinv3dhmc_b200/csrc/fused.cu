@@ -9,32 +9,32 @@
 //
 // Persistent kernel, one CTA per SM (cooperative launch => co-resident).  CTA b owns the column strip
 // [b W, (b+1) W) for every row: its slice of x and of the adjoint accumulator live in registers.
-// Rows stream through a 4-slot shared-memory ring filled by 1-D TMA bulk copies
-// (cp.async.bulk ... mbarrier::complete_tx), ~2 rows (2 x 56 KB at M = 2^20) in flight per SM.
-//   phase 1 (row i)     : partial dot of the strip with x, published as two self-validating 8-byte
-//                         words {value bits 0..31 | tag, value bits 32..63 | tag} (no fence, no flag);
-//   phase 2 (row i - 2) : every CTA polls the 148 pairs of that row (the poll is issued an iteration
-//                         early, its L2 round trip hides under the arithmetic), sums them in a fixed
-//                         order (identical bits on every CTA), forms e and adds
-//                         e * row-strip -- read from SHARED memory, not from HBM -- to its accumulator;
-//                         the slot is then refilled with row i + 2.
-// Round 2: a row waiting for its d_j no longer occupies a ring slot.  One iteration after its forward
-// dot the strip is copied from shared memory into 28 registers per thread and the slot is handed
-// straight back to the TMA unit, so TWO to THREE rows (112 - 170 KB) are in flight per SM instead of
-// one (the ring used to hold row i, the two rows waiting for their hand-off, and a single landing
-// slot: DRAM at 62 % of peak, latency-exposed); the adjoint update reads the registers.
+// Rows arrive in a 4-slot shared-memory ring filled by 1-D TMA bulk copies
+// (cp.async.bulk ... mbarrier::complete_tx), two to three rows (56 KB each at M = 2^20) in flight per SM.
+//   iteration i, row i     : partial dot of the strip with x (four accumulator chains), published as two
+//                            self-validating 8-byte words {value bits 0..31 | tag, bits 32..63 | tag}
+//                            (no fence, no flag; each word is single-copy atomic, both must carry the tag);
+//   iteration i, row i - 2 : every CTA has polled the 148 pairs of that row (the poll is issued an
+//                            iteration early, its L2 round trip hides under the arithmetic), sums them in
+//                            a fixed order (identical bits on every CTA), forms e and adds e * row-strip
+//                            -- held in REGISTERS since iteration i - 1 -- to its accumulator;
+//   iteration i, row i - 1 : its strip moves from shared memory into 28 registers per thread and the
+//                            slot goes straight back to the TMA unit (row i + 3).
+// Synchronisation inside the CTA: one full barrier per iteration; the hand-offs to thread 0 (publish,
+// re-arm the TMA) are named barriers on which the other seven warps only arrive.
 // No atomics (a same-address counter would serialise 148 L2 atomics per row), no grid-wide barrier:
-// a CTA only ever waits for rows published two iterations earlier.  What was tried and measured
-// slower on B200 (4096 x 2^20, two-pass 9.5 ms, this kernel 6.8 ms): release/acquire flags instead of
-// tagged pairs (14.7 ms: a MEMBAR per row on the critical path), consuming a row one iteration after
-// its publication (10.9 ms: every poll misses), two CTAs per SM with half strips (10.3 ms: the
-// hand-off traffic grows with the square of the CTA count), a dedicated TMA producer warp with
-// mbarrier slot release (10.5 ms), publishing at the end of the iteration (12.3 ms).  The kernel is
-// bound by the per-row hand-off chain of its single CTA per SM (ncu: short-scoreboard and barrier
-// stalls; DRAM at 62 % of peak), not by bandwidth.  DRAM traffic per evaluation is
-// 8 N M bytes instead of 16 N M; the result is deterministic (fixed strip ownership and summation
-// order).  Rounding differs from the two-pass form at the 1e-16 * |mean s| / |Aw^T r| level (~1e-14),
-// far inside the 1e-9 parity bar of the trajectories.
+// a CTA only ever waits for rows published two iterations earlier.  Measured on B200 (4096 x 2^20,
+// two-pass kernels 9.5 ms): round 1 (rows waited in the ring, two full barriers, one dot chain)
+// 6.8 ms = 0.77 of the measured copy bandwidth on DRAM bytes; retained row in registers 6.5 ms;
+// + arrive/sync hand-offs, four dot chains, prefetched fix / dobs 5.41 ms = 6.35 TB/s = 0.97 (c5, 16 384
+// rows: 23.6 ms = 0.89).  Tried and slower (round 1): release/acquire flags instead of tagged words
+// (14.7 ms: a MEMBAR per row on the critical path), consuming a row one iteration after its publication
+// (10.9 ms: every poll misses), two CTAs per SM with half strips (10.3 ms: the hand-off traffic grows
+// with the square of the CTA count), a dedicated TMA producer warp with mbarrier slot release (10.5 ms),
+// publishing at the end of the iteration (12.3 ms).  DRAM traffic per evaluation is 8 N M bytes instead
+// of 16 N M (ncu: 34.38 GB read at 4096 x 2^20); the result is deterministic (fixed strip ownership and
+// summation order).  Rounding differs from the two-pass form at the 1e-16 * |mean s| / |Aw^T r| level
+// (~1e-14), far inside the 1e-9 parity bar of the trajectories.
 #include <algorithm>
 #include <stdlib.h>
 #include <string.h>
