@@ -159,8 +159,6 @@ def test_200_samples_match_reference(case, tmp_path, monkeypatch):
 
 @pytest.mark.parametrize("case", ["c3_Damping", "c3_MS"])
 def test_200_samples_match_reference_c3(case, tmp_path, monkeypatch):
-    from oracle import oracle_np as onp
-
     g = c2h.load(case)
     model, geo, init, apr = build_model(case, g, monkeypatch, tmp_path)
     # (1) the GPU's own kernel: identical decisions, values within the near field's libm sensitivity

@@ -15,7 +15,6 @@ kernels, the conventions are checked against the oracle restatement in tests/tes
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import sys
