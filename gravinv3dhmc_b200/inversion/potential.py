@@ -354,6 +354,8 @@ class JointModule(GravMagModule):
                  njobs=1, mangle=(90, 0), wavelet=False, **kwargs):
         from ..utils import ang2vec, dircos
 
+        if kwargs.pop("shard", None) is not None:
+            raise NotImplementedError("JointModule is a single-GPU model (the block kernel is not row-sharded)")
         self.group = kwargs.pop("group", None)
         self.verbose = kwargs.pop("verbose", True)
         self.timing = {}
